@@ -1,8 +1,10 @@
 // engine.cu -- host side of the C ABI declared in include/llama_q4_b200.h.
 //
-// Mirrors the reference's host wrappers (llama2_q4.cu:207-432) one for one, but every launch goes to
-// the sm_100a kernels in kernels_sm100.cuh.  No CPU fallback exists: without a CUDA device the calls
-// fail loudly.
+// Mirrors the reference's host wrappers (llama2_q4.cu:207-432) one for one.  The decode step is ONE
+// launch of the persistent op-interpreter kernel (interp_sm100.cuh) over a device op table; every
+// operator of the API is the same kernel run over a single inline op.  Shapes the persistent kernel does
+// not take (K % 64 != 0 and the like) go to the generic kernels in kernels_sm100.cuh.  No CPU fallback
+// exists: without a CUDA device the calls fail loudly.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -11,9 +13,11 @@
 #include <algorithm>
 #include <map>
 #include <string>
+#include <vector>
 
 #include "lq4_types.h"
 #include "kernels_sm100.cuh"
+#include "interp_sm100.cuh"
 #include "synth.h"
 #include "../../include/llama_q4_b200.h"
 
@@ -30,21 +34,36 @@ struct RopeKey {
     }
 };
 
-constexpr int MAX_GRAPHS = 8;   // llama2_q4.cu:342
+// launch geometry of the persistent kernel
+struct Plan {
+    int nwc = 0, nslots = 0, slot_bytes = 0, scratch_bytes = 0;
+    size_t smem = 0;
+};
+
+// cached per RunState: the device op table of a whole decode step
+struct NetPlan {
+    Plan plan;
+    Op* d_ops = nullptr;
+    int nops = 0;              // including the trailing OP_ARGMAX
+    half* kraw = nullptr;      // un-rotated k row of the current step (consumed by OP_ATTN)
+    std::vector<char> key;     // Config + pointers the table was built from
+    bool ok = false;           // false: some shape is not supported by the persistent kernel
+};
 
 struct Engine {
     bool inited = false;
     int device = 0;
     int sm_count = 0;
+    int max_smem = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    int opt_pdl = 1;        // programmatic dependent launch between the fused kernels
-    int opt_fused = 1;      // run_llama_network: fused 5-kernel layer (1) or op-by-op like the reference (0)
-    int opt_graphs = 1;     // llama2_q4.cu:33 USE_CUDA_GRAPHS
+    int opt_pdl = 1;        // generic per-op kernels only
+    int opt_fused = 1;      // run_llama_network: one persistent launch per token (1) or op-by-op like the reference (0)
+    int opt_nwc = 0;        // consumer warps per CTA; 0 = choose per model
+    int opt_nslots = 8;     // target number of ring slots
     std::map<RopeKey, float2*> rope_tabs;
-    cudaGraphExec_t graph_exec[MAX_GRAPHS] = {};
-    bool graph_captured[MAX_GRAPHS] = {};
-    const void* graph_owner = nullptr;     // RunState the cached graphs were captured for
+    std::map<const void*, NetPlan> nets;
+    unsigned* sync = nullptr;
     std::map<const void*, void*> arenas;   // Transformer* -> device arena (loader)
     char err[512] = {0};
 };
@@ -79,11 +98,16 @@ void ensure_init() {
         exit(EXIT_FAILURE);
     }
     g.sm_count = prop.multiProcessorCount;
+    g.max_smem = (int)prop.sharedMemPerBlockOptin;
     if (!g.stream) { LQ4_CHECK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking)); g.own_stream = true; }
     const char* env;
     if ((env = getenv("LQ4_PDL"))) g.opt_pdl = atoi(env);
     if ((env = getenv("LQ4_FUSED"))) g.opt_fused = atoi(env);
-    if ((env = getenv("LQ4_GRAPHS"))) g.opt_graphs = atoi(env);
+    if ((env = getenv("LQ4_NWC"))) g.opt_nwc = atoi(env);
+    if ((env = getenv("LQ4_NSLOTS"))) g.opt_nslots = std::max(2, atoi(env));
+    LQ4_CHECK(cudaMalloc((void**)&g.sync, 2 * sizeof(unsigned)));
+    LQ4_CHECK(cudaMemset(g.sync, 0, 2 * sizeof(unsigned)));
+    LQ4_CHECK(cudaFuncSetAttribute(interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g.max_smem));
     g.inited = true;
 }
 
@@ -122,6 +146,7 @@ void allow_smem(K kernel, size_t bytes) {
     }
 }
 
+// ------------------------------------------------------------------------------- generic kernels (odd shapes)
 size_t gemv_smem(int K) { return (size_t)(((K + 1023) & ~1023) + 32) * sizeof(float); }
 
 template <int KIND>
@@ -152,53 +177,127 @@ float2* rope_table(float theta, int head_size, int seq_len) {
     return tab;
 }
 
-size_t attn_smem(int head_size, int max_seq) {
-    return (size_t)(head_size + 32 + 4 + ((max_seq + 3) & ~3) + 32 * head_size) * sizeof(float);
-}
-
-void launch_attention(half* out, const half* q, const half* kc, const half* vc, half* att, int num_heads,
-                      int head_size, int kv_mul, int max_seq_len, const int* pPos, bool pdl) {
-    if (head_size % 32 != 0 || head_size > 256) unsupported();
-    if (max_seq_len > MAX_SEQ_LEN_SMEM_KERNEL) {
-        // the reference switches to softmax_kernel_no_smem here (llama2_q4.cu:276-279), whose fp16
-        // rounding of exp() differs; that variant is scope row f2 and not built yet.
-        fprintf(stderr, "lq4: sequence bins above %d are not supported yet\n", MAX_SEQ_LEN_SMEM_KERNEL);
-        exit(EXIT_FAILURE);
-    }
-    AttnParams p;
-    p.out = out; p.q = q; p.kcache = kc; p.vcache = vc; p.att_out = att;
-    p.head_size = head_size; p.kv_mul = kv_mul; p.kv_stride = (num_heads * head_size) / kv_mul;
-    p.pPos = pPos;
-    p.alpha = (float)(1.0 / sqrt((double)head_size));     // llama2_q4.cu:273
-    p.max_seq = max_seq_len;
-    const size_t smem = attn_smem(head_size, max_seq_len);
-    allow_smem(attention_kernel, smem);
-    launch(attention_kernel, dim3(num_heads), dim3(kAttnThreads), smem, pdl, p);
-}
-
-void launch_classifier(half* out, const half* x, const half* norm_w, const half* w, int n, int d, int w_row_stride,
-                       float alpha, bool pdl) {
-    ClsParams p;
-    p.x = x; p.norm_w = norm_w; p.w = w; p.out = out; p.x_norm_out = nullptr;
-    p.n = n; p.d = d; p.w_row_stride = w_row_stride; p.alpha = alpha;
-    const size_t smem = (size_t)(((n / 2 + 3) & ~3) + 32) * sizeof(float);
-    allow_smem(gemv_f16_kernel, smem);
-    const int groups = (d + kClsRows - 1) / kClsRows;
-    int blocks = (groups + kClsThreads / 32 - 1) / (kClsThreads / 32);
-    blocks = std::min(blocks, 2 * g.sm_count);
-    launch(gemv_f16_kernel, dim3(blocks), dim3(kClsThreads), smem, pdl, p);
-}
-
 long time_in_ms() {   // llama2_q4.cu:400-405
     struct timespec time;
     timespec_get(&time, TIME_UTC);
     return time.tv_sec * 1000 + time.tv_nsec / 1000000;
 }
 
-void destroy_graphs() {
-    for (int i = 0; i < MAX_GRAPHS; i++)
-        if (g.graph_captured[i]) { cudaGraphExecDestroy(g.graph_exec[i]); g.graph_captured[i] = false; }
-    g.graph_owner = nullptr;
+// ------------------------------------------------------------------------------- persistent kernel: plans and ops
+int attn_scratch_bytes(int head_size, int max_seq) {
+    const int floats = 2 * head_size + ((max_seq + 3) & ~3) + 32 * head_size;
+    return (floats * 4 + 127) & ~127;
+}
+
+// ring geometry for `nwc` consumer warps, `scratch` bytes of attention scratch and ops whose smallest
+// schedulable piece (one unit of columns) is `min_slot` bytes
+bool make_plan(Plan& pl, int nwc, int scratch, int min_slot) {
+    pl.nwc = nwc;
+    pl.scratch_bytes = scratch;
+    const int fixed = kCtrlBytes + nwc * kHandBytes + scratch;
+    const int ring = g.max_smem - fixed;
+    if (ring <= 0) return false;
+    int slot = (ring / g.opt_nslots) & ~127;
+    const int need = (min_slot + 127) & ~127;
+    if (slot < need) slot = need;
+    pl.slot_bytes = slot;
+    pl.nslots = ring / slot;
+    if (pl.nslots > 32) pl.nslots = 32;
+    if (pl.nslots < 2) return false;
+    pl.smem = (size_t)fixed + (size_t)pl.nslots * slot;
+    return true;
+}
+
+bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+int q4_unit(int K) {
+    const int G = (K + 127) / 128, zh = (G + 7) / 8;
+    int u = 2;
+    while (((u * zh * 4) % 16) || ((u * G * 2) % 16)) u += 2;
+    return u;
+}
+int q4_col_total_bytes(int K) {
+    const int G = (K + 127) / 128, zh = (G + 7) / 8;
+    return K / 2 + G * 2 + zh * 4;
+}
+
+// fills the shape-derived fields of a q4 op; false when the persistent kernel cannot take it
+bool q4_op_shape(Op& op, int K, const int* ncols, int nseg, bool dual) {
+    if (K % 64 != 0 || K < 64 || K > kMaxConsumerWarps * 1024) return false;
+    op.K = K;
+    op.T = (K + 1023) / 1024;
+    op.unit = q4_unit(K);
+    op.nseg = nseg;
+    for (int s = 0; s < nseg; s++) {
+        if (ncols[s] % op.unit) return false;
+        if (!aligned16(op.seg[s].w) || !aligned16(op.seg[s].z) || !aligned16(op.seg[s].s)) return false;
+    }
+    if (dual && ncols[0] != ncols[1]) return false;
+    return true;
+}
+int q4_min_slot(const Op& op) { return op.unit * q4_col_total_bytes(op.K) * (op.kind == OP_FFN ? 2 : 1); }
+void q4_set_jc(Op& op, const Plan& pl) {
+    const int per_col = q4_col_total_bytes(op.K) * (op.kind == OP_FFN ? 2 : 1);
+    op.jc = (pl.slot_bytes / per_col) / op.unit * op.unit;
+}
+
+bool cls_op_shape(Op& op, int n, int d, int row_stride) {
+    if ((n & 7) || (row_stride & 7) || n > kMaxConsumerWarps * 1024 || !aligned16(op.seg[0].w)) return false;
+    op.K = n;
+    op.T = (n + 1023) / 1024;
+    op.unit = 1;
+    op.nseg = 1;
+    op.seg[0].ncols = d;
+    op.row_stride = row_stride;
+    return true;
+}
+int cls_min_slot(const Op& op) { return op.K * 2; }
+void cls_set_jc(Op& op, const Plan& pl) { op.jc = pl.slot_bytes / (op.K * 2); }
+
+void set_seg(Seg& sg, const QWeight* w, half* out, int ncols, int loff, int pos_stride) {
+    sg.w = w->weight; sg.z = w->zeros; sg.s = reinterpret_cast<const uint16_t*>(w->scales);
+    sg.out = out; sg.ncols = ncols; sg.loff = loff; sg.pos_stride = pos_stride; sg.pad_ = 0;
+}
+
+void launch_interp(const Plan& pl, const Op* d_ops, int nops, const Op* one, const int* pPos, int write_token,
+                   bool cooperative, int grid) {
+    InterpParams P;
+    memset(&P, 0, sizeof P);
+    P.ops = d_ops; P.nops = nops;
+    P.nwc = pl.nwc; P.nslots = pl.nslots; P.slot_bytes = pl.slot_bytes; P.scratch_bytes = pl.scratch_bytes;
+    P.write_token = write_token;
+    P.sync = g.sync; P.pPos = pPos;
+    if (one) P.one = *one;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(32 * (pl.nwc + 1));
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = g.stream;
+    cudaLaunchAttribute attr[1];
+    if (cooperative) {
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    cudaError_t e = cudaLaunchKernelEx(&cfg, interp_kernel, P);
+    if (e != cudaSuccess) { set_err("interp_kernel launch", e); exit(EXIT_FAILURE); }
+}
+
+// one op through the persistent kernel (operator API)
+void run_single(Op& op, int min_slot, int scratch, const int* pPos, bool is_cls) {
+    Plan pl;
+    int nwc = g.opt_nwc > 0 ? g.opt_nwc : 12;
+    if (op.kind <= OP_CLS && nwc < op.T) nwc = op.T;
+    nwc = std::min(nwc, kMaxConsumerWarps);
+    if (!make_plan(pl, nwc, scratch, min_slot)) unsupported();
+    if (op.kind == OP_CLS) cls_set_jc(op, pl);
+    else if (op.kind <= OP_FFN) q4_set_jc(op, pl);
+    (void)is_cls;
+    int grid = g.sm_count;
+    if (op.kind == OP_ATTN) grid = std::min(g.sm_count, op.n_heads);
+    if (op.kind == OP_ARGMAX) grid = 1;
+    launch_interp(pl, nullptr, 1, &op, pPos, -1, false, grid);
 }
 
 }  // namespace
@@ -220,7 +319,6 @@ void lq4_set_stream(void* s) {
     if (g.own_stream && g.stream) cudaStreamDestroy(g.stream);
     g.stream = (cudaStream_t)s;
     g.own_stream = false;
-    destroy_graphs();
 }
 int lq4_stream_synchronize(void) {
     ensure_init();
@@ -231,12 +329,19 @@ int lq4_stream_synchronize(void) {
 }
 const char* lq4_last_error(void) { return g.err; }
 int lq4_sm_count(void) { ensure_init(); return g.sm_count; }
+
+static void drop_net_plans() {
+    for (auto& kv : g.nets) { cudaFree(kv.second.d_ops); cudaFree(kv.second.kraw); }
+    g.nets.clear();
+}
+
 void lq4_set_option(const char* name, int value) {
     ensure_init();
     if (!strcmp(name, "pdl")) g.opt_pdl = value;
     else if (!strcmp(name, "fused")) g.opt_fused = value;
-    else if (!strcmp(name, "graphs")) g.opt_graphs = value;
-    destroy_graphs();
+    else if (!strcmp(name, "nwc")) { g.opt_nwc = value; cudaStreamSynchronize(g.stream); drop_net_plans(); }
+    else if (!strcmp(name, "nslots")) { g.opt_nslots = std::max(2, value); cudaStreamSynchronize(g.stream); drop_net_plans(); }
+    else if (!strcmp(name, "graphs")) { /* the decode step is a single launch: nothing to capture */ }
 }
 
 // ---------------------------------------------------------------------------------- operator API
@@ -245,23 +350,41 @@ void lq4_rmsnorm(half* o, half* x, half* weight, int size) {
     rmsnorm_kernel<<<1, 1024, 0, g.stream>>>(o, x, weight, size);
 }
 
-void lq4_matmul_fp16(half* xout, half* x, half* w, int n, int d, int batch, int x_stride, int w_stride,
-                     int op_stride, int w_row_stride, float alpha) {
+void lq4_matmul_fp16(half* xout, half* x, half* w, int n, int d, int batch, int x_stride, int w_stride, int op_stride,
+                     int w_row_stride, float alpha) {
     ensure_init();
     if ((n & 7) || (d & 7)) unsupported();
     if (w_row_stride == -1) w_row_stride = n;
-    for (int b = 0; b < batch; b++)   // the reference batches through blockIdx.y; the only caller uses batch 1
-        launch_classifier(xout + (size_t)b * op_stride, x + (size_t)b * x_stride, nullptr, w + (size_t)b * w_stride, n, d,
-                          w_row_stride, alpha, false);
+    for (int b = 0; b < batch; b++) {   // the reference batches through blockIdx.y; the only caller uses batch 1
+        Op op;
+        memset(&op, 0, sizeof op);
+        op.kind = OP_CLS;
+        op.seg[0].w = reinterpret_cast<const uint32_t*>(w + (size_t)b * w_stride);
+        op.seg[0].out = xout + (size_t)b * op_stride;
+        op.x = x + (size_t)b * x_stride;
+        op.alpha = alpha;
+        if (!cls_op_shape(op, n, d, w_row_stride)) unsupported();
+        run_single(op, cls_min_slot(op), 0, nullptr, true);
+    }
 }
 
 void lq4_matmul_q4(half* xout, half* x, const QWeight* w, int inpSize, int opSize, int accum, int loff, int* pPos) {
     ensure_init();
     check_q4_shape(inpSize, opSize);
+    Op op;
+    memset(&op, 0, sizeof op);
+    op.kind = OP_GEMV;
+    op.x = x; op.accum = accum;
+    const bool cache_row = (loff != -1);
+    set_seg(op.seg[0], w, xout, opSize, cache_row ? loff : 0, cache_row ? opSize : 0);
+    if (q4_op_shape(op, inpSize, &opSize, 1, false)) {
+        run_single(op, q4_min_slot(op), 0, cache_row ? pPos : nullptr, false);
+        return;
+    }
     GemvParams p = {};
     p.x = x; p.K = inpSize;
     p.m[0] = qw_view(w); p.n[0] = opSize; p.out[0] = xout;
-    p.accum = accum; p.loff = loff; p.pPos = (loff != -1) ? pPos : nullptr;
+    p.accum = accum; p.loff = loff; p.pPos = cache_row ? pPos : nullptr;
     launch_gemv<GEMV_PLAIN>(p, opSize / 4, false);
 }
 
@@ -269,6 +392,18 @@ void lq4_qkv_matvec(half* q, half* key_cache, half* value_cache, half* x, const 
                     const QWeight* vw, int inpSize, int opSize, int loff, int* pPos) {
     ensure_init();
     check_q4_shape(inpSize, opSize);
+    Op op;
+    memset(&op, 0, sizeof op);
+    op.kind = OP_GEMV;
+    op.x = x;
+    set_seg(op.seg[0], qw, q, opSize, 0, 0);
+    set_seg(op.seg[1], kw, key_cache, opSize, loff, opSize);
+    set_seg(op.seg[2], vw, value_cache, opSize, loff, opSize);
+    const int nc[3] = {opSize, opSize, opSize};
+    if (q4_op_shape(op, inpSize, nc, 3, false)) {
+        run_single(op, q4_min_slot(op), 0, pPos, false);
+        return;
+    }
     GemvParams p = {};
     p.x = x; p.K = inpSize;
     p.m[0] = qw_view(qw); p.m[1] = qw_view(kw); p.m[2] = qw_view(vw);
@@ -281,6 +416,17 @@ void lq4_qkv_matvec(half* q, half* key_cache, half* value_cache, half* x, const 
 void lq4_ffn_matvec_silu(half* xout, half* x, const QWeight* gate_w, const QWeight* up_w, int inpSize, int opSize) {
     ensure_init();
     check_q4_shape(inpSize, opSize);
+    Op op;
+    memset(&op, 0, sizeof op);
+    op.kind = OP_FFN;
+    op.x = x;
+    set_seg(op.seg[0], gate_w, xout, opSize, 0, 0);
+    set_seg(op.seg[1], up_w, xout, opSize, 0, 0);
+    const int nc[2] = {opSize, opSize};
+    if (q4_op_shape(op, inpSize, nc, 2, true)) {
+        run_single(op, q4_min_slot(op), 0, nullptr, false);
+        return;
+    }
     GemvParams p = {};
     p.x = x; p.K = inpSize;
     p.m[0] = qw_view(gate_w); p.m[1] = qw_view(up_w);
@@ -295,10 +441,30 @@ void lq4_rope_rotation(half* q, half* k, int num_heads, int num_kv_heads, int he
     rope_kernel<<<num_heads, head_size / 2, 0, g.stream>>>(q, k, num_kv_heads, head_size, pPos, loff, rope_theta);
 }
 
+static void fill_attn_op(Op& op, half* output, half* q, half* key_cache, half* value_cache, half* att, int num_heads,
+                         int head_size, int kv_mul, int max_seq_len) {
+    if (head_size % 32 != 0 || head_size > 256) unsupported();
+    if (max_seq_len > MAX_SEQ_LEN_SMEM_KERNEL) {
+        // the reference switches to softmax_kernel_no_smem here (llama2_q4.cu:276-279), whose fp16
+        // rounding of exp() differs; that variant is scope row f2 and not built yet.
+        fprintf(stderr, "lq4: sequence bins above %d are not supported yet\n", MAX_SEQ_LEN_SMEM_KERNEL);
+        exit(EXIT_FAILURE);
+    }
+    op.kind = OP_ATTN;
+    op.q = q; op.kcache = key_cache; op.vcache = value_cache; op.att_out = att; op.attn_out = output;
+    op.n_heads = num_heads; op.head_size = head_size; op.kv_mul = kv_mul;
+    op.kv_stride = (num_heads * head_size) / kv_mul;
+    op.max_seq = max_seq_len;
+    op.att_alpha = (float)(1.0 / sqrt((double)head_size));     // llama2_q4.cu:273
+}
+
 void lq4_multi_head_attention(half* output, half* q, half* key_cache, half* value_cache, half* att, int num_heads,
                               int head_size, int kv_mul, int max_seq_len, int* pPos) {
     ensure_init();
-    launch_attention(output, q, key_cache, value_cache, att, num_heads, head_size, kv_mul, max_seq_len, pPos, false);
+    Op op;
+    memset(&op, 0, sizeof op);
+    fill_attn_op(op, output, q, key_cache, value_cache, att, num_heads, head_size, kv_mul, max_seq_len);
+    run_single(op, 256, attn_scratch_bytes(head_size, max_seq_len), pPos, false);
 }
 
 // ---------------------------------------------------------------------------------- forward pass
@@ -334,71 +500,164 @@ static void run_network_unfused(int* pPos, Config* p, RunState* s, TransformerWe
     lq4_matmul_fp16(s->logits, x, w->wcls, p->dim, p->vocab_size, 1, 0, 0, 0, -1, 1.0f);
 }
 
-static void run_network_fused(int* pPos, Config* p, RunState* s, TransformerWeights* w, int seq_len_bin,
-                              const float2* rope_tab) {
-    // Same dataflow in 5 kernels per layer: [embed+]RMSNorm+QKV+RoPE | attention | O+residual |
-    // RMSNorm+gate/up+SiLU | down+residual, then RMSNorm+classifier.
-    const int dim = p->dim, hidden_dim = p->hidden_dim;
+// consumer warps per CTA for a model: every op needs T <= nwc; prefer the count that keeps the most warps
+// busy weighted by the bytes each op streams
+static int choose_nwc(const std::vector<std::pair<int, double>>& t_bytes) {
+    if (g.opt_nwc > 0) return std::min(g.opt_nwc, kMaxConsumerWarps);
+    int tmax = 1;
+    for (auto& tb : t_bytes) tmax = std::max(tmax, tb.first);
+    int best = -1;
+    double best_cost = 0;
+    for (int n = std::max(tmax, 8); n <= kMaxConsumerWarps; n++) {
+        double cost = 0;
+        for (auto& tb : t_bytes) cost += tb.second / ((n / tb.first) * tb.first);
+        if (best < 0 || cost < best_cost * 0.999) { best = n; best_cost = cost; }
+    }
+    return best < 0 ? kMaxConsumerWarps : best;
+}
+
+// Builds (once per RunState) the op table of a whole decode step:
+//   per layer  [embed+]RMSNorm+q|k|v  ->  RoPE+attention  ->  o+residual  ->  RMSNorm+gate/up+SiLU  ->  down+residual
+//   then       RMSNorm+classifier  ->  argmax
+static NetPlan& get_net_plan(Config* p, RunState* s, TransformerWeights* w) {
+    std::vector<char> key(sizeof(Config) + sizeof(RunState) + sizeof(TransformerWeights));
+    memcpy(key.data(), p, sizeof(Config));
+    memcpy(key.data() + sizeof(Config), s, sizeof(RunState));
+    memcpy(key.data() + sizeof(Config) + sizeof(RunState), w, sizeof(TransformerWeights));
+    NetPlan& np = g.nets[(const void*)s];
+    if (np.key == key) return np;
+    if (np.d_ops) { LQ4_CHECK(cudaStreamSynchronize(g.stream)); cudaFree(np.d_ops); cudaFree(np.kraw); np.d_ops = nullptr; np.kraw = nullptr; }
+    np.key = key;
+    np.ok = false;
+
+    const int dim = p->dim, hidden = p->hidden_dim;
     const int head_size = dim / p->n_heads;
     const int kv_dim = (p->dim * p->n_kv_heads) / p->n_heads;
     const int kv_mul = p->n_heads / p->n_kv_heads;
-    const bool pdl = g.opt_pdl != 0;
-    check_q4_shape(dim, dim);
-    check_q4_shape(dim, kv_dim);
-    check_q4_shape(dim, hidden_dim);
-    check_q4_shape(hidden_dim, dim);
-    if (head_size % 4 != 0) unsupported();
-    for (int l = 0; l < p->n_layers; l++) {
+    if (head_size % 32 != 0 || head_size > 256 || (head_size & 1) || p->seq_len > MAX_SEQ_LEN_SMEM_KERNEL) return np;
+    LQ4_CHECK(cudaMalloc((void**)&np.kraw, sizeof(half) * kv_dim));
+    const float2* rope_tab = rope_table(p->rope_theta, head_size, p->seq_len);
+
+    std::vector<Op> ops;
+    bool ok = true;
+    for (int l = 0; l < p->n_layers && ok; l++) {
         PerLayerWeight& L = w->layers[l];
         const int loff = l * p->seq_len * kv_dim;
         {
-            GemvParams a = {};
-            a.x = s->x; a.norm_w = L.rms_att_weight; a.K = dim;
-            if (l == 0) { a.emb_table = w->token_embedding_table; a.tokens = s->shared_data->tokens; a.x_copy = s->x; }
-            a.m[0] = qw_view(&L.wq_q); a.m[1] = qw_view(&L.wq_k); a.m[2] = qw_view(&L.wq_v);
-            a.n[0] = dim; a.n[1] = kv_dim; a.n[2] = kv_dim;
-            a.out[0] = s->q; a.out[1] = s->key_cache; a.out[2] = s->value_cache;
-            a.loff = loff; a.pPos = pPos;
-            a.rope_tab = rope_tab; a.head_size = head_size;
-            launch_gemv<GEMV_QKV>(a, (dim + 2 * kv_dim) / 4, pdl && l > 0);
-        }
-        launch_attention(s->xb, s->q, s->key_cache + loff, s->value_cache + loff, nullptr, p->n_heads, head_size,
-                         kv_mul, seq_len_bin, pPos, pdl);
-        {
-            GemvParams a = {};
-            a.x = s->xb; a.K = dim;
-            a.m[0] = qw_view(&L.wq_o); a.n[0] = dim; a.out[0] = s->x;
-            a.accum = 1; a.loff = -1;
-            launch_gemv<GEMV_PLAIN>(a, dim / 4, pdl);
+            Op op; memset(&op, 0, sizeof op);
+            op.kind = OP_GEMV;
+            op.x = s->x; op.norm_w = L.rms_att_weight;
+            if (l == 0) { op.emb = w->token_embedding_table; op.tokens = s->shared_data->tokens; op.x_copy = s->x; }
+            op.sync_before = (l > 0);
+            set_seg(op.seg[0], &L.wq_q, s->q, dim, 0, 0);
+            set_seg(op.seg[1], &L.wq_k, np.kraw, kv_dim, 0, 0);                     // rotated into the cache by OP_ATTN
+            set_seg(op.seg[2], &L.wq_v, s->value_cache, kv_dim, loff, kv_dim);
+            const int nc[3] = {dim, kv_dim, kv_dim};
+            ok = ok && q4_op_shape(op, dim, nc, 3, false);
+            ops.push_back(op);
         }
         {
-            GemvParams a = {};
-            a.x = s->x; a.norm_w = L.rms_ffn_weight; a.K = dim;
-            a.m[0] = qw_view(&L.wq_gate); a.m[1] = qw_view(&L.wq_up);
-            a.n[0] = hidden_dim; a.out[0] = s->hb; a.loff = -1;
-            launch_gemv<GEMV_FFN>(a, hidden_dim / 2, pdl);
+            Op op; memset(&op, 0, sizeof op);
+            fill_attn_op(op, s->xb, s->q, s->key_cache + loff, s->value_cache + loff, nullptr, p->n_heads, head_size, kv_mul,
+                         p->seq_len);
+            op.kraw = np.kraw; op.rope_tab = rope_tab;
+            op.sync_before = 1;
+            ops.push_back(op);
         }
         {
-            GemvParams a = {};
-            a.x = s->hb; a.K = hidden_dim;
-            a.m[0] = qw_view(&L.wq_down); a.n[0] = dim; a.out[0] = s->x;
-            a.accum = 1; a.loff = -1;
-            launch_gemv<GEMV_PLAIN>(a, dim / 4, pdl);
+            Op op; memset(&op, 0, sizeof op);
+            op.kind = OP_GEMV; op.x = s->xb; op.accum = 1; op.sync_before = 1;
+            set_seg(op.seg[0], &L.wq_o, s->x, dim, 0, 0);
+            ok = ok && q4_op_shape(op, dim, &dim, 1, false);
+            ops.push_back(op);
+        }
+        {
+            Op op; memset(&op, 0, sizeof op);
+            op.kind = OP_FFN; op.x = s->x; op.norm_w = L.rms_ffn_weight; op.sync_before = 1;
+            set_seg(op.seg[0], &L.wq_gate, s->hb, hidden, 0, 0);
+            set_seg(op.seg[1], &L.wq_up, s->hb, hidden, 0, 0);
+            const int nc[2] = {hidden, hidden};
+            ok = ok && q4_op_shape(op, dim, nc, 2, true);
+            ops.push_back(op);
+        }
+        {
+            Op op; memset(&op, 0, sizeof op);
+            op.kind = OP_GEMV; op.x = s->hb; op.accum = 1; op.sync_before = 1;
+            set_seg(op.seg[0], &L.wq_down, s->x, dim, 0, 0);
+            ok = ok && q4_op_shape(op, hidden, &dim, 1, false);
+            ops.push_back(op);
         }
     }
-    launch_classifier(s->logits, s->x, w->rms_final_weight, w->wcls, dim, p->vocab_size, dim, 1.0f, pdl);
+    {
+        Op op; memset(&op, 0, sizeof op);
+        op.kind = OP_CLS; op.x = s->x; op.norm_w = w->rms_final_weight; op.sync_before = 1;
+        op.seg[0].w = reinterpret_cast<const uint32_t*>(w->wcls);
+        op.seg[0].out = s->logits;
+        op.alpha = 1.0f;
+        ok = ok && cls_op_shape(op, dim, p->vocab_size, dim);
+        ops.push_back(op);
+    }
+    {
+        Op op; memset(&op, 0, sizeof op);
+        op.kind = OP_ARGMAX; op.sync_before = 1;
+        op.logits = s->logits; op.vocab = p->vocab_size;
+        op.tokens_out = &(s->shared_data->tokens[0]);
+        op.pos_host = &(s->shared_data->pos);
+        op.pos_dev = s->pos;
+        op.write_token = 1;
+        ops.push_back(op);
+    }
+    if (!ok) return np;
+
+    std::vector<std::pair<int, double>> tb;
+    int min_slot = 0;
+    for (auto& op : ops) {
+        if (op.kind <= OP_FFN) {
+            int cols = 0;
+            for (int i = 0; i < op.nseg; i++) cols += op.seg[i].ncols;
+            tb.push_back({op.T, (double)cols * q4_col_total_bytes(op.K)});
+            min_slot = std::max(min_slot, q4_min_slot(op));
+        } else if (op.kind == OP_CLS) {
+            tb.push_back({op.T, (double)op.seg[0].ncols * op.K * 2});
+            min_slot = std::max(min_slot, cls_min_slot(op));
+        }
+    }
+    const int nwc = choose_nwc(tb);
+    for (auto& op : ops)
+        if (op.kind <= OP_CLS && op.T > nwc) return np;
+    if (!make_plan(np.plan, nwc, attn_scratch_bytes(head_size, p->seq_len), min_slot)) return np;
+    for (auto& op : ops) {
+        if (op.kind <= OP_FFN) q4_set_jc(op, np.plan);
+        else if (op.kind == OP_CLS) cls_set_jc(op, np.plan);
+        if (op.kind <= OP_CLS && op.jc < op.unit) return np;
+    }
+    // the persistent kernel needs one co-resident CTA per SM
+    int per_sm = 0;
+    LQ4_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, interp_kernel, 32 * (nwc + 1), np.plan.smem));
+    if (per_sm < 1) return np;
+    np.nops = (int)ops.size();
+    LQ4_CHECK(cudaMalloc((void**)&np.d_ops, sizeof(Op) * ops.size()));
+    LQ4_CHECK(cudaMemcpy(np.d_ops, ops.data(), sizeof(Op) * ops.size(), cudaMemcpyHostToDevice));
+    np.ok = true;
+    return np;
+}
+
+// one persistent launch: the forward pass, and the greedy sampler too when with_argmax
+static bool run_network_fused(int* pPos, Config* p, RunState* s, TransformerWeights* w, bool with_argmax, int write_token) {
+    NetPlan& np = get_net_plan(p, s, w);
+    if (!np.ok) return false;
+    if (pPos != s->pos) {
+        fprintf(stderr, "lq4: run_llama_network expects pPos == RunState::pos\n");
+        exit(EXIT_FAILURE);
+    }
+    launch_interp(np.plan, np.d_ops, with_argmax ? np.nops : np.nops - 1, nullptr, pPos, write_token, true, g.sm_count);
+    return true;
 }
 
 void lq4_run_llama_network(int* pPos, Config* p, RunState* s, TransformerWeights* w, int seq_len_bin) {
     ensure_init();
-    if (g.opt_fused) {
-        // the table must exist before a capture starts; run_transformer guarantees that, a direct caller
-        // gets it built here (a synchronising call, so not legal inside capture on first use)
-        const float2* tab = rope_table(p->rope_theta, p->dim / p->n_heads, p->seq_len);
-        run_network_fused(pPos, p, s, w, seq_len_bin, tab);
-    } else {
-        run_network_unfused(pPos, p, s, w, seq_len_bin);
-    }
+    if (g.opt_fused && run_network_fused(pPos, p, s, w, false, -1)) return;
+    run_network_unfused(pPos, p, s, w, seq_len_bin);
 }
 
 void lq4_build_sampler(Sampler* sampler, int vocab_size, float temperature, float topp, unsigned long long rng_seed) {
@@ -424,50 +683,47 @@ static unsigned int random_u32(unsigned long long* state) {   // sampler.h:31-37
     return (unsigned int)((*state * 0x2545F4914F6CDD1Dull) >> 32);
 }
 
-void lq4_sample(Sampler* sampler, RunState* s, int gen_token, void* cuda_stream) {
-    ensure_init();
-    (void)random_u32(&sampler->rng_state);   // the reference burns one draw per step (sampler.h:45)
+static void check_greedy(Sampler* sampler, int gen_token) {
     if (sampler->temperature != 0.0f && gen_token) {
         // temperature / top-p sampling (sampler.h:51-81) is scope row f3: not built yet, fail loudly
         fprintf(stderr, "lq4: only greedy sampling (-t 0) is implemented\n");
         exit(EXIT_FAILURE);
     }
+}
+
+void lq4_sample(Sampler* sampler, RunState* s, int gen_token, void* cuda_stream) {
+    ensure_init();
+    (void)random_u32(&sampler->rng_state);   // the reference burns one draw per step (sampler.h:45)
+    check_greedy(sampler, gen_token);
     argmax_kernel<<<1, 1024, 0, (cudaStream_t)cuda_stream>>>(s->logits, sampler->vocab_size,
                                                              &(s->shared_data->tokens[0]), &(s->shared_data->pos),
                                                              s->pos, nullptr, gen_token != 0);
 }
 
-static void run_forward_graphed(Config* p, RunState* s, TransformerWeights* w, int seq_len) {
-    if (!g.opt_graphs) { lq4_run_llama_network(s->pos, p, s, w, seq_len); return; }
-    // length bins 128,256,...,8192, last bin = max seq len (llama2_q4.cu:356-360)
-    int graphIndex, seq_len_bin = 128;
-    for (graphIndex = 0; graphIndex < MAX_GRAPHS - 1; seq_len_bin *= 2, graphIndex++)
-        if (seq_len <= seq_len_bin) break;
-    if ((seq_len > seq_len_bin) || (graphIndex == MAX_GRAPHS - 1)) seq_len_bin = p->seq_len;
-    if (g.graph_owner != (const void*)s) { destroy_graphs(); g.graph_owner = s; }
-    if (!g.graph_captured[graphIndex]) {
-        if (g.opt_fused) (void)rope_table(p->rope_theta, p->dim / p->n_heads, p->seq_len);   // before capture
-        cudaGraph_t graph = {};
-        LQ4_CHECK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
-        lq4_run_llama_network(s->pos, p, s, w, seq_len_bin);
-        LQ4_CHECK(cudaStreamEndCapture(g.stream, &graph));
-        LQ4_CHECK(cudaGraphInstantiate(&g.graph_exec[graphIndex], graph, 0));
-        cudaGraphDestroy(graph);
-        g.graph_captured[graphIndex] = true;
+// forward + sample; seq_len_bin only matters to the op-by-op path
+static void forward_and_sample(int gen_token, Config* p, RunState* s, TransformerWeights* w, int copyLogits,
+                               Sampler* pSampler, int seq_len_bin) {
+    if (g.opt_fused && !copyLogits) {
+        check_greedy(pSampler, gen_token);
+        if (run_network_fused(s->pos, p, s, w, true, gen_token != 0)) {
+            (void)random_u32(&pSampler->rng_state);
+            return;
+        }
     }
-    LQ4_CHECK(cudaGraphLaunch(g.graph_exec[graphIndex], g.stream));
-}
-
-void lq4_run_transformer(int gen_token, Config* p, RunState* s, TransformerWeights* w, int copyLogits,
-                         Sampler* pSampler) {
-    ensure_init();
-    const int seq_len = s->shared_data->pos + 1;       // llama2_q4.cu:354
-    run_forward_graphed(p, s, w, seq_len);
+    lq4_run_llama_network(s->pos, p, s, w, seq_len_bin);
     if (copyLogits) {                                  // llama2_q4.cu:377-382 (perplexity mode)
         float* pOutput = s->logits_array + (size_t)p->vocab_size * s->shared_data->pos;
         convert_fp16_to_fp32_kernel<<<divUp(p->vocab_size, 128), 128, 0, g.stream>>>(pOutput, s->logits, p->vocab_size);
     }
     lq4_sample(pSampler, s, gen_token, g.stream);
+}
+
+void lq4_run_transformer(int gen_token, Config* p, RunState* s, TransformerWeights* w, int copyLogits,
+                         Sampler* pSampler) {
+    ensure_init();
+    // the reference picks a CUDA graph by length bin here (llama2_q4.cu:354-372); this engine's step is a
+    // single launch whose work depends only on the device-side position, so there is nothing to select
+    forward_and_sample(gen_token, p, s, w, copyLogits, pSampler, p->seq_len);
 }
 
 // ---------------------------------------------------------------------------------- loader
@@ -578,12 +834,15 @@ int lq4_build_transformer(Transformer* t, const char* checkpoint_path, int perpl
     if (perplexity) LQ4_CHECK(cudaMalloc((void**)&s->logits_array, sizeof(float) * (size_t)p->seq_len * vocab));
     (void)rope_table(p->rope_theta, p->dim / p->n_heads, p->seq_len);
     LQ4_CHECK(cudaDeviceSynchronize());   // the memsets above ran on the legacy stream
+    (void)get_net_plan(p, s, w);          // op table of the decode step
     return 0;
 }
 
 void lq4_free_transformer(Transformer* t) {
-    destroy_graphs();
     RunState* s = &t->state;
+    cudaStreamSynchronize(g.stream);
+    auto np = g.nets.find((const void*)s);
+    if (np != g.nets.end()) { cudaFree(np->second.d_ops); cudaFree(np->second.kraw); g.nets.erase(np); }
     cudaFree(s->x); cudaFree(s->xb); cudaFree(s->pos); cudaFree(s->hb); cudaFree(s->q); cudaFree(s->att);
     cudaFree(s->logits); cudaFree(s->key_cache); cudaFree(s->value_cache); cudaFreeHost(s->shared_data);
     if (s->logits_array) cudaFree(s->logits_array);
@@ -614,12 +873,11 @@ int lq4_step(Transformer* t, Sampler* sampler, int gen_token, half* logits_out, 
     return pos;
 }
 
-// Enqueue one forward + sample without touching the host copy of the position: the caller states the
-// sequence length (pos+1) that selects the graph bin.  Used by the pipelined loop and by bench.py.
+// Enqueue one forward + sample without touching the host copy of the position.  seq_len (= pos+1) is what
+// the reference's graph-bin selection needs (llama2_q4.cu:354-360); only the op-by-op path uses it here.
 void lq4_enqueue_step(Transformer* t, Sampler* sampler, int seq_len, int gen_token) {
     ensure_init();
-    run_forward_graphed(&t->config, &t->state, &t->weights, seq_len);
-    lq4_sample(sampler, &t->state, gen_token, g.stream);
+    forward_and_sample(gen_token, &t->config, &t->state, &t->weights, 0, sampler, std::max(seq_len, 1));
 }
 
 int lq4_generate_tokens(Transformer* t, Sampler* sampler, const int* prompt_tokens, int n_prompt, int steps,
@@ -650,7 +908,7 @@ int lq4_generate_tokens(Transformer* t, Sampler* sampler, const int* prompt_toke
             pos++;
         }
     } else {
-        // The position and the sampled token live on the device (argmax_kernel writes both), so step
+        // The position and the sampled token live on the device (the sampler writes both), so step
         // pos+1 can be enqueued before step pos has finished; the host only trails behind to read
         // tokens.  Events mark the end of each step.
         cudaEvent_t ev[2];
@@ -660,9 +918,7 @@ int lq4_generate_tokens(Transformer* t, Sampler* sampler, const int* prompt_toke
         bool stop = false;
         while (pos < steps && !stop) {
             while (launched < steps && launched <= pos + 1) {
-                // bin selection needs the sequence length: known on the host without reading it back
-                run_forward_graphed(p, s, &t->weights, launched + 1);
-                lq4_sample(sampler, s, launched >= n_prompt - 1, g.stream);
+                forward_and_sample(launched >= n_prompt - 1, p, s, &t->weights, 0, sampler, launched + 1);
                 LQ4_CHECK(cudaEventRecord(ev[launched & 1], g.stream));
                 launched++;
             }

@@ -113,7 +113,12 @@ void* ref_state_ptr(int which) {
 }
 void ref_close() {
     if (!g_ref_open) return;
+    cudaStreamSynchronize(stream);
     free_transformer(&g_ref_t);
+    // the reference caches captured graphs in globals (llama2_q4.cu:342-344) and only drops them at the end
+    // of main (:713-716); do the same here, or the next model would replay graphs holding freed pointers
+    for (int i = 0; i < MAX_GRAPHS; i++)
+        if (graphCaptured[i]) { cudaGraphExecDestroy(cudaGraphInstance[i]); graphCaptured[i] = false; }
     g_ref_open = false;
 }
 

@@ -225,8 +225,13 @@ def test_rope_rotation(eng, nh, nkv, hs, theta):
         lib.lq4_rope_rotation(dq.data_ptr(), dk.data_ptr(), nh, nkv, hs, dp.data_ptr(), 0, theta)
         sync(lib)
         gq, gk = H.dev_u16(dq), H.dev_u16(dk)
-        assert H.ulp_diff_f16(gq, qo).max() <= 1
-        assert H.ulp_diff_f16(gk[pos * nkv * hs:(pos + 1) * nkv * hs], ko).max() <= 1
+        # vs the CPU oracle: host libm vs CUDA sinf/cosf differ by an fp32 ulp or so, and q0*c - q1*s can cancel, so
+        # the tolerance is absolute (2 fp16 ulps of the largest input); the bit-exact check is the reference below
+        def close(a, b, scale):
+            fa, fb = a.view(np.float16).astype(np.float32), b.view(np.float16).astype(np.float32)
+            return np.abs(fa - fb).max() <= 2.0 ** -9 * scale
+        assert close(gq, qo, float(np.abs(q.astype(np.float32)).max()))
+        assert close(gk[pos * nkv * hs:(pos + 1) * nkv * hs], ko, float(np.abs(kc.astype(np.float32)).max()))
         if r is not None:
             rq, rk = H.to_dev(q.view(np.uint16)), H.to_dev(kc.view(np.uint16))
             r.ref_rope(rq.data_ptr(), rk.data_ptr(), nh, nkv, hs, dp.data_ptr(), 0, theta)
