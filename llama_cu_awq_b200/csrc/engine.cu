@@ -34,9 +34,9 @@ struct RopeKey {
     }
 };
 
-// launch geometry of the persistent kernel
+// launch geometry of the persistent kernel (shared-memory map of interp_sm100.cuh)
 struct Plan {
-    int nwc = 0, nslots = 0, slot_bytes = 0, scratch_bytes = 0;
+    int nwc = 0, nslots = 0, slot_bytes = 0, meta_bytes = 0, xs_bytes = 0;
     size_t smem = 0;
 };
 
@@ -60,7 +60,8 @@ struct Engine {
     int opt_pdl = 1;        // generic per-op kernels only
     int opt_fused = 1;      // run_llama_network: one persistent launch per token (1) or op-by-op like the reference (0)
     int opt_nwc = 0;        // consumer warps per CTA; 0 = choose per model
-    int opt_nslots = 8;     // target number of ring slots
+    int opt_nslots = 0;     // cap on ring slots; 0 = as many as fit
+    int opt_slot_bytes = 0; // ring slot size; 0 = the largest minimum chunk of the model's ops
     std::map<RopeKey, float2*> rope_tabs;
     std::map<const void*, NetPlan> nets;
     unsigned* sync = nullptr;
@@ -104,7 +105,8 @@ void ensure_init() {
     if ((env = getenv("LQ4_PDL"))) g.opt_pdl = atoi(env);
     if ((env = getenv("LQ4_FUSED"))) g.opt_fused = atoi(env);
     if ((env = getenv("LQ4_NWC"))) g.opt_nwc = atoi(env);
-    if ((env = getenv("LQ4_NSLOTS"))) g.opt_nslots = std::max(2, atoi(env));
+    if ((env = getenv("LQ4_NSLOTS"))) g.opt_nslots = atoi(env);
+    if ((env = getenv("LQ4_SLOT_BYTES"))) g.opt_slot_bytes = atoi(env);
     LQ4_CHECK(cudaMalloc((void**)&g.sync, 2 * sizeof(unsigned)));
     LQ4_CHECK(cudaMemset(g.sync, 0, 2 * sizeof(unsigned)));
     LQ4_CHECK(cudaFuncSetAttribute(interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g.max_smem));
@@ -189,70 +191,77 @@ int attn_scratch_bytes(int head_size, int max_seq) {
     return (floats * 4 + 127) & ~127;
 }
 
-// ring geometry for `nwc` consumer warps, `scratch` bytes of attention scratch and ops whose smallest
-// schedulable piece (one unit of columns) is `min_slot` bytes
-bool make_plan(Plan& pl, int nwc, int scratch, int min_slot) {
+// Shared-memory plan for `nwc` consumer warps: a staging area of `xs` bytes (activations / attention scratch),
+// `meta` bytes of scales / zero points and as many ring slots of `slot` bytes as fit.
+bool make_plan(Plan& pl, int nwc, int xs, int meta, int slot) {
     pl.nwc = nwc;
-    pl.scratch_bytes = scratch;
-    const int fixed = kCtrlBytes + nwc * kHandBytes + scratch;
+    pl.xs_bytes = (xs + 127) & ~127;
+    pl.meta_bytes = (meta + 127) & ~127;
+    pl.slot_bytes = std::max(128, (slot + 127) & ~127);
+    const int fixed = kCtrlBytes + pl.xs_bytes + pl.meta_bytes;
     const int ring = g.max_smem - fixed;
     if (ring <= 0) return false;
-    int slot = (ring / g.opt_nslots) & ~127;
-    const int need = (min_slot + 127) & ~127;
-    if (slot < need) slot = need;
-    pl.slot_bytes = slot;
-    pl.nslots = ring / slot;
-    if (pl.nslots > 32) pl.nslots = 32;
-    if (pl.nslots < 2) return false;
-    pl.smem = (size_t)fixed + (size_t)pl.nslots * slot;
+    int n = ring / pl.slot_bytes;
+    if (g.opt_nslots > 0) n = std::min(n, g.opt_nslots);
+    n = std::min(n, kMaxSlots);
+    if (n < 4) return false;          // a task takes up to 4 slots
+    pl.nslots = n;
+    pl.smem = (size_t)fixed + (size_t)n * pl.slot_bytes;
     return true;
 }
 
 bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
-int q4_unit(int K) {
-    const int G = (K + 127) / 128, zh = (G + 7) / 8;
-    int u = 2;
-    while (((u * zh * 4) % 16) || ((u * G * 2) % 16)) u += 2;
-    return u;
-}
-int q4_col_total_bytes(int K) {
-    const int G = (K + 127) / 128, zh = (G + 7) / 8;
-    return K / 2 + G * 2 + zh * 4;
-}
-
 // fills the shape-derived fields of a q4 op; false when the persistent kernel cannot take it
 bool q4_op_shape(Op& op, int K, const int* ncols, int nseg, bool dual) {
-    if (K % 64 != 0 || K < 64 || K > kMaxConsumerWarps * 1024) return false;
+    if (K % 64 != 0 || K < 64) return false;
     op.K = K;
     op.T = (K + 1023) / 1024;
-    op.unit = q4_unit(K);
     op.nseg = nseg;
+    int total = 0;
     for (int s = 0; s < nseg; s++) {
-        if (ncols[s] % op.unit) return false;
+        if (ncols[s] % 8) return false;
         if (!aligned16(op.seg[s].w) || !aligned16(op.seg[s].z) || !aligned16(op.seg[s].s)) return false;
+        total += ncols[s];
     }
     if (dual && ncols[0] != ncols[1]) return false;
+    op.ntasks = dual ? ncols[0] / 2 : total / 4;
     return true;
 }
-int q4_min_slot(const Op& op) { return op.unit * q4_col_total_bytes(op.K) * (op.kind == OP_FFN ? 2 : 1); }
-void q4_set_jc(Op& op, const Plan& pl) {
-    const int per_col = q4_col_total_bytes(op.K) * (op.kind == OP_FFN ? 2 : 1);
-    op.jc = (pl.slot_bytes / per_col) / op.unit * op.unit;
-}
-
 bool cls_op_shape(Op& op, int n, int d, int row_stride) {
-    if ((n & 7) || (row_stride & 7) || n > kMaxConsumerWarps * 1024 || !aligned16(op.seg[0].w)) return false;
+    if ((n & 7) || (row_stride & 7) || (d & 3) || !aligned16(op.seg[0].w)) return false;
     op.K = n;
-    op.T = (n + 1023) / 1024;
-    op.unit = 1;
+    op.T = (n + 255) / 256;
     op.nseg = 1;
     op.seg[0].ncols = d;
+    op.ntasks = (d + 3) / 4;
     op.row_stride = row_stride;
     return true;
 }
-int cls_min_slot(const Op& op) { return op.K * 2; }
-void cls_set_jc(Op& op, const Plan& pl) { op.jc = pl.slot_bytes / (op.K * 2); }
+// bytes of the smallest ring chunk the op can be cut into (one column | one gate/up pair | one row)
+int op_min_chunk(const Op& op) {
+    if (op.kind == OP_CLS) return op.K * 2;
+    return (op.kind == OP_FFN ? 2 : 1) * q4_col_bytes(op.K);
+}
+// bytes of a whole warp-task (4 columns | 2 gate/up pairs | 4 rows)
+int op_task_bytes(const Op& op) { return op_min_chunk(op) * (op.kind == OP_FFN ? 2 : 4); }
+// cut the op's tasks into ring slots of `slot` bytes
+bool op_set_chunking(Op& op, int slot) {
+    const int per = op.kind == OP_FFN ? 2 : 4;      // chunks of minimum size per task
+    int cps = per;
+    while (cps >= 1 && cps * op_min_chunk(op) > slot) cps >>= 1;
+    if (cps < 1) return false;
+    op.cps = cps;
+    op.spt = per / cps;
+    return true;
+}
+int op_xs_bytes(const Op& op) { return op.kind == OP_CLS ? op.K * 2 : op.T * 4096; }
+int op_meta_bytes(const Op& op, int grid) {
+    if (op.kind == OP_CLS) return 0;
+    const int maxtasks = (op.ntasks + grid - 1) / grid;
+    const int cols = maxtasks * 4;                   // 4 columns, or 2 gate + 2 up columns, per task
+    return cols * (q4_groups(op.K) * 2 + q4_zh(op.K) * 4) + 64;
+}
 
 void set_seg(Seg& sg, const QWeight* w, half* out, int ncols, int loff, int pos_stride) {
     sg.w = w->weight; sg.z = w->zeros; sg.s = reinterpret_cast<const uint16_t*>(w->scales);
@@ -264,7 +273,7 @@ void launch_interp(const Plan& pl, const Op* d_ops, int nops, const Op* one, con
     InterpParams P;
     memset(&P, 0, sizeof P);
     P.ops = d_ops; P.nops = nops;
-    P.nwc = pl.nwc; P.nslots = pl.nslots; P.slot_bytes = pl.slot_bytes; P.scratch_bytes = pl.scratch_bytes;
+    P.nwc = pl.nwc; P.nslots = pl.nslots; P.slot_bytes = pl.slot_bytes; P.meta_bytes = pl.meta_bytes; P.xs_bytes = pl.xs_bytes;
     P.write_token = write_token;
     P.sync = g.sync; P.pPos = pPos;
     if (one) P.one = *one;
@@ -284,19 +293,26 @@ void launch_interp(const Plan& pl, const Op* d_ops, int nops, const Op* one, con
     if (e != cudaSuccess) { set_err("interp_kernel launch", e); exit(EXIT_FAILURE); }
 }
 
+int default_nwc() { return g.opt_nwc > 0 ? std::min(g.opt_nwc, kMaxConsumerWarps) : kMaxConsumerWarps; }
+
 // one op through the persistent kernel (operator API)
-void run_single(Op& op, int min_slot, int scratch, const int* pPos, bool is_cls) {
+void run_single(Op& op, const int* pPos) {
     Plan pl;
-    int nwc = g.opt_nwc > 0 ? g.opt_nwc : 12;
-    if (op.kind <= OP_CLS && nwc < op.T) nwc = op.T;
-    nwc = std::min(nwc, kMaxConsumerWarps);
-    if (!make_plan(pl, nwc, scratch, min_slot)) unsupported();
-    if (op.kind == OP_CLS) cls_set_jc(op, pl);
-    else if (op.kind <= OP_FFN) q4_set_jc(op, pl);
-    (void)is_cls;
-    int grid = g.sm_count;
-    if (op.kind == OP_ATTN) grid = std::min(g.sm_count, op.n_heads);
-    if (op.kind == OP_ARGMAX) grid = 1;
+    int grid = g.sm_count, xs = 0, meta = 0, slot = 128;
+    if (op.kind <= OP_CLS) {
+        grid = std::max(1, std::min(g.sm_count, op.ntasks));
+        xs = op_xs_bytes(op);
+        meta = op_meta_bytes(op, grid);
+        slot = g.opt_slot_bytes > 0 ? std::max(g.opt_slot_bytes, op_min_chunk(op)) : std::min(op_task_bytes(op), 16384);
+        slot = std::max(slot, op_min_chunk(op));
+        if (!op_set_chunking(op, slot)) unsupported();
+    } else if (op.kind == OP_ATTN) {
+        grid = std::min(g.sm_count, op.n_heads);
+        xs = attn_scratch_bytes(op.head_size, op.max_seq);
+    } else {
+        grid = 1;
+    }
+    if (!make_plan(pl, default_nwc(), xs, meta, slot)) unsupported();
     launch_interp(pl, nullptr, 1, &op, pPos, -1, false, grid);
 }
 
@@ -340,7 +356,8 @@ void lq4_set_option(const char* name, int value) {
     if (!strcmp(name, "pdl")) g.opt_pdl = value;
     else if (!strcmp(name, "fused")) g.opt_fused = value;
     else if (!strcmp(name, "nwc")) { g.opt_nwc = value; cudaStreamSynchronize(g.stream); drop_net_plans(); }
-    else if (!strcmp(name, "nslots")) { g.opt_nslots = std::max(2, value); cudaStreamSynchronize(g.stream); drop_net_plans(); }
+    else if (!strcmp(name, "slot_bytes")) { g.opt_slot_bytes = value; cudaStreamSynchronize(g.stream); drop_net_plans(); }
+    else if (!strcmp(name, "nslots")) { g.opt_nslots = value; cudaStreamSynchronize(g.stream); drop_net_plans(); }
     else if (!strcmp(name, "graphs")) { /* the decode step is a single launch: nothing to capture */ }
 }
 
@@ -364,7 +381,7 @@ void lq4_matmul_fp16(half* xout, half* x, half* w, int n, int d, int batch, int 
         op.x = x + (size_t)b * x_stride;
         op.alpha = alpha;
         if (!cls_op_shape(op, n, d, w_row_stride)) unsupported();
-        run_single(op, cls_min_slot(op), 0, nullptr, true);
+        run_single(op, nullptr);
     }
 }
 
@@ -378,7 +395,7 @@ void lq4_matmul_q4(half* xout, half* x, const QWeight* w, int inpSize, int opSiz
     const bool cache_row = (loff != -1);
     set_seg(op.seg[0], w, xout, opSize, cache_row ? loff : 0, cache_row ? opSize : 0);
     if (q4_op_shape(op, inpSize, &opSize, 1, false)) {
-        run_single(op, q4_min_slot(op), 0, cache_row ? pPos : nullptr, false);
+        run_single(op, cache_row ? pPos : nullptr);
         return;
     }
     GemvParams p = {};
@@ -401,7 +418,7 @@ void lq4_qkv_matvec(half* q, half* key_cache, half* value_cache, half* x, const 
     set_seg(op.seg[2], vw, value_cache, opSize, loff, opSize);
     const int nc[3] = {opSize, opSize, opSize};
     if (q4_op_shape(op, inpSize, nc, 3, false)) {
-        run_single(op, q4_min_slot(op), 0, pPos, false);
+        run_single(op, pPos);
         return;
     }
     GemvParams p = {};
@@ -424,7 +441,7 @@ void lq4_ffn_matvec_silu(half* xout, half* x, const QWeight* gate_w, const QWeig
     set_seg(op.seg[1], up_w, xout, opSize, 0, 0);
     const int nc[2] = {opSize, opSize};
     if (q4_op_shape(op, inpSize, nc, 2, true)) {
-        run_single(op, q4_min_slot(op), 0, nullptr, false);
+        run_single(op, nullptr);
         return;
     }
     GemvParams p = {};
@@ -464,7 +481,7 @@ void lq4_multi_head_attention(half* output, half* q, half* key_cache, half* valu
     Op op;
     memset(&op, 0, sizeof op);
     fill_attn_op(op, output, q, key_cache, value_cache, att, num_heads, head_size, kv_mul, max_seq_len);
-    run_single(op, 256, attn_scratch_bytes(head_size, max_seq_len), pPos, false);
+    run_single(op, pPos);
 }
 
 // ---------------------------------------------------------------------------------- forward pass
@@ -498,22 +515,6 @@ static void run_network_unfused(int* pPos, Config* p, RunState* s, TransformerWe
     }
     lq4_rmsnorm(x, x, w->rms_final_weight, dim);
     lq4_matmul_fp16(s->logits, x, w->wcls, p->dim, p->vocab_size, 1, 0, 0, 0, -1, 1.0f);
-}
-
-// consumer warps per CTA for a model: every op needs T <= nwc; prefer the count that keeps the most warps
-// busy weighted by the bytes each op streams
-static int choose_nwc(const std::vector<std::pair<int, double>>& t_bytes) {
-    if (g.opt_nwc > 0) return std::min(g.opt_nwc, kMaxConsumerWarps);
-    int tmax = 1;
-    for (auto& tb : t_bytes) tmax = std::max(tmax, tb.first);
-    int best = -1;
-    double best_cost = 0;
-    for (int n = std::max(tmax, 8); n <= kMaxConsumerWarps; n++) {
-        double cost = 0;
-        for (auto& tb : t_bytes) cost += tb.second / ((n / tb.first) * tb.first);
-        if (best < 0 || cost < best_cost * 0.999) { best = n; best_cost = cost; }
-    }
-    return best < 0 ? kMaxConsumerWarps : best;
 }
 
 // Builds (once per RunState) the op table of a whole decode step:
@@ -609,28 +610,18 @@ static NetPlan& get_net_plan(Config* p, RunState* s, TransformerWeights* w) {
     }
     if (!ok) return np;
 
-    std::vector<std::pair<int, double>> tb;
-    int min_slot = 0;
+    int xs = attn_scratch_bytes(head_size, p->seq_len), meta = 0, slot = 0;
     for (auto& op : ops) {
-        if (op.kind <= OP_FFN) {
-            int cols = 0;
-            for (int i = 0; i < op.nseg; i++) cols += op.seg[i].ncols;
-            tb.push_back({op.T, (double)cols * q4_col_total_bytes(op.K)});
-            min_slot = std::max(min_slot, q4_min_slot(op));
-        } else if (op.kind == OP_CLS) {
-            tb.push_back({op.T, (double)op.seg[0].ncols * op.K * 2});
-            min_slot = std::max(min_slot, cls_min_slot(op));
-        }
+        if (op.kind > OP_CLS) continue;
+        xs = std::max(xs, op_xs_bytes(op));
+        meta = std::max(meta, op_meta_bytes(op, g.sm_count));
+        slot = std::max(slot, op_min_chunk(op));
     }
-    const int nwc = choose_nwc(tb);
+    if (g.opt_slot_bytes > 0) slot = std::max(slot, g.opt_slot_bytes);
+    const int nwc = default_nwc();
+    if (!make_plan(np.plan, nwc, xs, meta, slot)) return np;
     for (auto& op : ops)
-        if (op.kind <= OP_CLS && op.T > nwc) return np;
-    if (!make_plan(np.plan, nwc, attn_scratch_bytes(head_size, p->seq_len), min_slot)) return np;
-    for (auto& op : ops) {
-        if (op.kind <= OP_FFN) q4_set_jc(op, np.plan);
-        else if (op.kind == OP_CLS) cls_set_jc(op, np.plan);
-        if (op.kind <= OP_CLS && op.jc < op.unit) return np;
-    }
+        if (op.kind <= OP_CLS && !op_set_chunking(op, np.plan.slot_bytes)) return np;
     // the persistent kernel needs one co-resident CTA per SM
     int per_sm = 0;
     LQ4_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, interp_kernel, 32 * (nwc + 1), np.plan.smem));

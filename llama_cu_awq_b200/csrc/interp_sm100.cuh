@@ -1,21 +1,23 @@
-// interp_sm100.cuh -- the persistent decode kernel for sm_100a ("op interpreter").
+// interp_sm100.cuh -- the persistent decode kernel for sm_100a ("op interpreter"), v3.
 //
 // One launch walks a table of ops (the whole per-token forward pass of llama2_q4.cu:286-340 plus the
 // greedy sampler, or a single op for the operator API) with ONE CTA PER SM:
 //
-//   * a PRODUCER warp streams every weight byte the CTA will need through a ring of shared-memory slots
-//     with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx).  Weights never depend on
-//     activations, so the producer runs ahead across op boundaries and grid barriers: HBM keeps
-//     streaming while the consumers wait on a dependency.
-//   * CONSUMER warps are arranged as SYSTOLIC PIPELINES along K.  Stage i of a pipeline owns the
-//     reference's "trip" i (k in [1024 i, 1024 i + 1024), gpu_kernels.h:176-201) and keeps its slice of
-//     the activation vector in REGISTERS for the whole op, so the inner loop reads nothing but packed
-//     weights from shared memory.  The fp32 accumulator of a column is handed from stage to stage
-//     through shared memory, which keeps every per-lane FMA chain of the reference in its original
-//     order: results are bit-identical.
-//   * one thread owns TWO reference lanes (2j, 2j+1) of one column, so that one packed FFMA2
-//     (fma.rn.f32x2) advances both chains with a natural (x[k], x[k+32]) register pair, and the
-//     per-group scale / zero-point preparation is shared by 64 weights.  A half-warp is one column.
+//   * a PRODUCER warp streams every weight byte the CTA will need with 1-D TMA bulk copies
+//     (cp.async.bulk + mbarrier complete_tx) into PER-CONSUMER-WARP rings of shared-memory slots.
+//     Weights never depend on activations, so the producer runs ahead across op boundaries and grid
+//     barriers: HBM keeps streaming while the consumers wait on a dependency.  Producer lane l feeds
+//     consumer warp l, so no consumer ever waits for another warp's data.
+//   * each CONSUMER warp owns whole output columns: a warp-task is 4 columns (two per half-warp) of an
+//     INT4 matrix, or 2 gate/up column pairs, or 4 classifier rows, streamed trip by trip
+//     (1024 k per trip, the reference's loop trip, gpu_kernels.h:176-201).  There is NO inter-warp
+//     synchronisation inside an op: the accumulators of a column stay in one thread's registers from the
+//     first trip to the last, which keeps every per-lane FMA chain of the reference in its original order
+//     (results are bit-identical) and makes the consumers issue-bound instead of latency-bound.
+//   * one thread owns TWO reference lanes (2j, 2j+1) of two columns: one packed FFMA2 (fma.rn.f32x2)
+//     advances both lane chains of a column with a natural (x[k], x[k+32]) register pair that is read
+//     from shared memory once and used for both columns.  The activation vector is staged per op into
+//     shared memory as fp32 pairs in exactly that order (after the fused RMSNorm).
 //   * ops are separated by a grid-wide barrier (release/acquire counter in global memory) only where
 //     the dataflow needs one.
 //
@@ -56,9 +58,10 @@ struct Seg {
 struct Op {
     int kind;
     int K;                 // input length (OP_CLS: n)
-    int T;                 // pipeline stages = ceil(K / 1024)
-    int unit;              // CTA column ranges start on multiples of `unit` (16-byte alignment of the meta copies)
-    int jc;                // columns (OP_CLS: rows) per ring slot
+    int T;                 // trips: ceil(K / 1024)  (OP_CLS: ceil(n / 256))
+    int cps;               // columns (gate/up pairs, rows) per ring slot: 4, 2 or 1
+    int spt;               // ring slots per warp-task
+    int ntasks;            // warp-tasks of the whole op (4 columns | 2 gate/up pairs | 4 rows each)
     int nseg;
     int accum;             // OP_GEMV: out = half(sum + float(out))  (residual, gpu_kernels.h:229-230)
     int sync_before;       // grid barrier before the consumers read this op's inputs
@@ -96,8 +99,9 @@ struct InterpParams {
     int nops;
     int nwc;               // consumer warps per CTA (blockDim.x = 32 * (nwc + 1))
     int nslots;            // ring slots
-    int slot_bytes;        // bytes per slot (multiple of 128)
-    int scratch_bytes;     // attention scratch
+    int slot_bytes;        // bytes per ring slot (multiple of 128)
+    int meta_bytes;        // scale/zero staging area
+    int xs_bytes;          // activation staging area (aliased with the attention scratch)
     int write_token;       // overrides Op::write_token of OP_ARGMAX when >= 0
     unsigned* sync;        // [2] grid barrier counter, exit counter (zero between launches)
     const int* pPos;       // device position
@@ -105,11 +109,13 @@ struct InterpParams {
 };
 
 constexpr int kMaxConsumerWarps = 15;
+constexpr int kMaxSlots = 128;
 constexpr int kBarAll = 13;        // named barrier: all consumer warps
-constexpr int kCtrlBytes = 1024;   // mbarriers + reduction scratch
-constexpr int kHandBytes = 512;    // per consumer warp: float2[2][32]
-constexpr unsigned kSpinLimit = 1u << 27;
-
+constexpr int kCtrlBytes = 4096;   // mbarriers (first 2 KB) + reduction scratch (at 3 KB)
+constexpr int kRedOffset = 3072;
+constexpr unsigned kSpinLimit = 1u << 24;
+constexpr unsigned long long kWaitLimitNs = 2000000000ull;   // a wait longer than 2 s is a protocol bug: trap
+constexpr int kLapOffset = 2048;   // per-slot release counters
 // ------------------------------------------------------------------------------------------------
 // PTX: mbarrier, bulk copy, named barriers, coherent loads
 // ------------------------------------------------------------------------------------------------
@@ -129,11 +135,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
                  : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     return done != 0;
 }
+// non-blocking probe (try_wait may suspend the whole warp for a system-defined time when the phase is not complete)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0;
+}
 // Bounded spin: a protocol bug must abort the launch (trap), never hang the device.
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    unsigned spins = 0;
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = global_ns();
     while (!mbar_try_wait(bar, parity))
-        if (++spins > kSpinLimit) asm volatile("trap;");
+        if (global_ns() - t0 > kWaitLimitNs) asm volatile("trap;");
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
@@ -197,95 +216,107 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target,
     if (ctid == 0) {
         __threadfence();
         asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
-        unsigned v, spins = 0;
+        unsigned v;
+        const unsigned long long t0 = global_ns();
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-            if (++spins > kSpinLimit) asm volatile("trap;");
+            if (v < target && global_ns() - t0 > kWaitLimitNs) asm volatile("trap;");
         } while (v < target);
         __threadfence();
     }
     named_bar(kBarAll, nthreads);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Work split: CTA b of nb owns columns [c0, c1) of the op's concatenated column space.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int op_total_cols(const Op& op) {
-    int n = 0;
-    for (int s = 0; s < op.nseg; s++) n += op.seg[s].ncols;
-    return (op.kind == OP_FFN) ? op.seg[0].ncols : n;
+__device__ __forceinline__ void lds_v2_b64(uint32_t addr, unsigned long long& a, unsigned long long& b) {
+    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
 }
-__device__ __forceinline__ void cta_range(const Op& op, int b, int nb, int& c0, int& c1) {
-    const int units = op_total_cols(op) / op.unit;
-    c0 = (int)(((long long)units * b) / nb) * op.unit;
-    c1 = (int)(((long long)units * (b + 1)) / nb) * op.unit;
+__device__ __forceinline__ void sts_v4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-struct Chunk {
-    int seg;       // matrix
-    int col;       // first column inside the matrix
-    int n;         // columns
-};
-// next chunk starting at column c of the concatenated space (never crosses a matrix boundary)
-__device__ __forceinline__ Chunk next_chunk(const Op& op, int c, int c1) {
-    Chunk ch;
-    int base = 0, s = 0;
-    if (op.kind != OP_FFN) {
-        while (s + 1 < op.nseg && c >= base + op.seg[s].ncols) { base += op.seg[s].ncols; s++; }
-    }
-    const int seg_end = base + op.seg[s].ncols;
-    int n = op.jc;
-    if (n > c1 - c) n = c1 - c;
-    if (n > seg_end - c) n = seg_end - c;
-    ch.seg = s; ch.col = c - base; ch.n = n;
-    return ch;
+__device__ __forceinline__ void sts_v4_u32(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-// slot layout of a q4 chunk of n columns: [weights (A)][weights (B, FFN only)][scales A][scales B][zeros A][zeros B]
-__device__ __forceinline__ int q4_col_bytes(int K) { return K >> 1; }
-__device__ __forceinline__ int q4_groups(int K) { return (K + 127) >> 7; }
-__device__ __forceinline__ int q4_zh(int K) { return (q4_groups(K) + 7) >> 3; }
 
 // ------------------------------------------------------------------------------------------------
-// Producer: one lane issues, in op order, every bulk copy this CTA will consume.
+// Geometry shared by the producer, the consumers and the host planner
 // ------------------------------------------------------------------------------------------------
-__device__ void producer_loop(const InterpParams& P, const Op* ops, uint8_t* ring, uint32_t full0, uint32_t empty0) {
+__host__ __device__ __forceinline__ int q4_groups(int K) { return (K + 127) >> 7; }
+__host__ __device__ __forceinline__ int q4_zh(int K) { return (q4_groups(K) + 7) >> 3; }
+__host__ __device__ __forceinline__ int q4_col_bytes(int K) { return K >> 1; }
+
+// CTA b of nb owns warp-tasks [t0, t1) of the op
+__device__ __forceinline__ void cta_task_range(const Op& op, int b, int nb, int& t0, int& t1) {
+    t0 = (int)(((long long)op.ntasks * b) / nb);
+    t1 = (int)(((long long)op.ntasks * (b + 1)) / nb);
+}
+// GEMV: column c of the concatenated column space -> (matrix, column inside it)
+__device__ __forceinline__ void gemv_locate(const Op& op, int c, int& seg, int& col) {
+    int s = 0;
+    while (s + 1 < op.nseg && c >= op.seg[s].ncols) { c -= op.seg[s].ncols; s++; }
+    seg = s; col = c;
+}
+
+struct Smem {            // shared-memory map (shared-window addresses)
+    uint32_t bars;       // full[S], empty[S]
+    uint32_t laps;       // [S] releases of each slot so far (consumers only)
+    uint32_t xs;         // activation staging / attention scratch
+    uint32_t meta;       // scales and zero points of this CTA's columns for the current op
+    uint32_t ring;       // [S][slot_bytes]
+    int S, slot_bytes;
+    __device__ __forceinline__ uint32_t full(int s) const { return bars + (uint32_t)s * 8; }
+    __device__ __forceinline__ uint32_t empty(int s) const { return bars + (uint32_t)(S + s) * 8; }
+    __device__ __forceinline__ uint32_t slot(int s) const { return ring + (uint32_t)s * slot_bytes; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Producer: one lane issues, in op order, every bulk copy this CTA will consume.  The ring is a FIFO of
+// fixed-size slots; a warp-task takes `spt` consecutive slots, each filled by one copy (two for gate/up) of a
+// run of whole columns -- adjacent columns are contiguous in the reference layout, so a slot is one or two
+// multi-KB bulk copies (the TMA unit sustains ~1 copy per 70 cycles per SM: copies must be large).
+// ------------------------------------------------------------------------------------------------
+__device__ void producer_loop(const InterpParams& P, const Op* ops, const Smem& sm) {
     uint64_t policy;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-    unsigned seq = 0;
+    int slot = 0;
+    uint32_t phase = 0;
     for (int o = 0; o < P.nops; o++) {
         const Op& op = ops[o];
         if (op.kind > OP_CLS) continue;
-        int c0, c1;
-        cta_range(op, blockIdx.x, gridDim.x, c0, c1);
-        for (int c = c0; c < c1;) {
-            const Chunk ch = next_chunk(op, c, c1);
-            const unsigned slot = seq % P.nslots, use = seq / P.nslots;
-            mbar_wait(empty0 + 8 * slot, (use & 1) ^ 1);
-            const uint32_t dst = smem_u32(ring + (size_t)slot * P.slot_bytes);
-            const uint32_t bar = full0 + 8 * slot;
-            if (op.kind == OP_CLS) {
-                const uint32_t bytes = (uint32_t)ch.n * op.K * 2;
-                mbar_arrive_expect_tx(bar, bytes);
-                if (op.row_stride == op.K) {
-                    bulk_g2s(dst, (const half*)op.seg[0].w + (size_t)ch.col * op.row_stride, bytes, bar, policy);
+        int t0, t1;
+        cta_task_range(op, blockIdx.x, gridDim.x, t0, t1);
+        const int cps = op.cps, spt = op.spt;
+        const size_t colb = (op.kind == OP_CLS) ? (size_t)op.K * 2 : (size_t)q4_col_bytes(op.K);
+        for (int task = t0; task < t1; task++) {
+            int seg = 0, col = 0;
+            if (op.kind == OP_GEMV) gemv_locate(op, task * 4, seg, col);
+            for (int i = 0; i < spt; i++) {
+                mbar_wait(sm.empty(slot), phase ^ 1);
+                const uint32_t dst = sm.slot(slot), bar = sm.full(slot);
+                if (op.kind == OP_GEMV) {
+                    const uint32_t bytes = (uint32_t)(cps * colb);
+                    mbar_arrive_expect_tx(bar, bytes);
+                    bulk_g2s(dst, (const uint8_t*)op.seg[seg].w + (size_t)(col + i * cps) * colb, bytes, bar, policy);
+                } else if (op.kind == OP_FFN) {      // slot: [gate cps columns][up cps columns]
+                    const uint32_t bytes = (uint32_t)(cps * colb);
+                    mbar_arrive_expect_tx(bar, 2 * bytes);
+                    const size_t off = (size_t)(task * 2 + i * cps) * colb;
+                    bulk_g2s(dst, (const uint8_t*)op.seg[0].w + off, bytes, bar, policy);
+                    bulk_g2s(dst + bytes, (const uint8_t*)op.seg[1].w + off, bytes, bar, policy);
                 } else {
-                    for (int r = 0; r < ch.n; r++)
-                        bulk_g2s(dst + r * op.K * 2, (const half*)op.seg[0].w + (size_t)(ch.col + r) * op.row_stride,
-                                 op.K * 2, bar, policy);
+                    const int row = task * 4 + i * cps;
+                    int rows = op.seg[0].ncols - row;
+                    if (rows > cps) rows = cps;
+                    if (rows < 0) rows = 0;
+                    mbar_arrive_expect_tx(bar, (uint32_t)(rows * colb));
+                    const half* w = (const half*)op.seg[0].w + (size_t)row * op.row_stride;
+                    if (op.row_stride == op.K) {
+                        if (rows > 0) bulk_g2s(dst, w, (uint32_t)(rows * colb), bar, policy);
+                    } else {
+                        for (int r = 0; r < rows; r++) bulk_g2s(dst + r * colb, w + (size_t)r * op.row_stride, (uint32_t)colb, bar, policy);
+                    }
                 }
-            } else {
-                const int nm = (op.kind == OP_FFN) ? 2 : 1;
-                const uint32_t wb = (uint32_t)ch.n * q4_col_bytes(op.K), sb = (uint32_t)ch.n * q4_groups(op.K) * 2,
-                               zb = (uint32_t)ch.n * q4_zh(op.K) * 4;
-                mbar_arrive_expect_tx(bar, nm * (wb + sb + zb));
-                for (int m = 0; m < nm; m++) {
-                    const Seg& sg = op.seg[(op.kind == OP_FFN) ? m : ch.seg];
-                    bulk_g2s(dst + m * wb, (const uint8_t*)sg.w + (size_t)ch.col * q4_col_bytes(op.K), wb, bar, policy);
-                    bulk_g2s(dst + nm * wb + m * sb, (const uint8_t*)sg.s + (size_t)ch.col * q4_groups(op.K) * 2, sb, bar, policy);
-                    bulk_g2s(dst + nm * (wb + sb) + m * zb, (const uint8_t*)sg.z + (size_t)ch.col * q4_zh(op.K) * 4, zb, bar, policy);
-                }
+                if (++slot == sm.S) { slot = 0; phase ^= 1; }
             }
-            seq++;
-            c += ch.n;
         }
     }
 }
@@ -295,15 +326,13 @@ __device__ void producer_loop(const InterpParams& P, const Op* ops, uint8_t* rin
 // ------------------------------------------------------------------------------------------------
 struct Ctx {
     const InterpParams* P;
-    uint8_t* ring;
-    uint32_t full0, empty0;   // shared addresses of the mbarrier arrays
+    Smem sm;
     float* red;               // 64 floats of reduction scratch
-    float2* hand;             // [nwc][2][32]
-    uint8_t* scratch;         // attention scratch
+    uint8_t* scratch;         // generic pointer to the xs area (attention scratch)
     int nwc, nthreads;        // consumer warps / threads
     int warp, lane, ctid;
     int pos;
-    unsigned seq;             // ring sequence number of the next chunk (same in every warp)
+    unsigned qbase;           // ring chunks of all ops before the current one (this CTA)
     unsigned nsync;           // grid barriers taken so far
 };
 
@@ -342,281 +371,343 @@ __device__ __forceinline__ uint32_t norm_h(uint32_t xh, uint32_t wh, float scale
     const float v = __fmul_rn(h2f_bits(xh), __fmul_rn(scale, h2f_bits(wh)));
     return f2h_bits(v);
 }
+__device__ __forceinline__ uint32_t word_of(const uint4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
 
-// ------------------------------------------------------------------------------------------------
-// INT4 GEMV / FFN consumer
-// ------------------------------------------------------------------------------------------------
-// One step = one column per half-warp (64 weights per thread).  `wcol` = shared address of the column's
-// packed weights, `scol` / `zcol` of its scales / zero words.  acc = (chain of reference lane 2j+swap,
-// chain of reference lane 2j+1-swap).
-__device__ __forceinline__ void q4_step(unsigned long long& acc, const unsigned long long (&xp)[32], uint32_t wcol,
-                                        uint32_t scol, uint32_t zcol, int stage, int j, int swap) {
-    const uint32_t wa_addr = wcol + stage * 512 + j * 32 + (swap ? 16 : 0);
-    const uint4 wa = lds_v4(wa_addr);
-    const uint4 wb = lds_v4(wa_addr ^ 16);
-    const uint32_t s16 = lds_u16(scol + (stage * 8 + (j >> 1)) * 2);
-    const uint32_t zw = lds_u32(zcol + stage * 4);
-    const uint32_t zp = ((zw >> ((j >> 1) * 4)) & 0xFu) | 0x6400u;            // fp16 bits of 1024 + z
-    const float nlo = fhfma_lo(zp, s16 ^ 0x8000u, 0.0f);                       // -(1024+z)*s, exact
-    const float nhi = fhfma_lo(0x6380u, s16, nlo);                             // -(64+z)*s = 960*s + nlo, exact
+// cooperative copy of `nwords` 32-bit words global -> shared (loads batched four deep per thread)
+__device__ __forceinline__ void copy_words(const Ctx& c, uint32_t dst, const uint32_t* src, int nwords) {
+    for (int base = c.ctid; base < nwords; base += 4 * c.nthreads) {
+        uint32_t v[4];
 #pragma unroll
-    for (int qi = 0; qi < 4; qi++) {
-        const uint32_t a = (qi == 0) ? wa.x : (qi == 1) ? wa.y : (qi == 2) ? wa.z : wa.w;
-        const uint32_t b = (qi == 0) ? wb.x : (qi == 1) ? wb.y : (qi == 2) ? wb.z : wb.w;
-        float da[8], db[8];
-        dequant8(da, a, s16, nlo, nhi);
-        dequant8(db, b, s16, nlo, nhi);
+        for (int r = 0; r < 4; r++) {
+            const int e = base + r * c.nthreads;
+            v[r] = (e < nwords) ? ldg_stream_u32(src + e) : 0u;
+        }
 #pragma unroll
-        for (int e = 0; e < 8; e++) ffma2_pk(acc, da[e], db[e], xp[qi * 8 + e]);
+        for (int r = 0; r < 4; r++) {
+            const int e = base + r * c.nthreads;
+            if (e < nwords) asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst + e * 4), "r"(v[r]) : "memory");
+        }
     }
 }
 
-__device__ void run_q4(Ctx& c, const Op& op) {
-    const int T = op.T, K = op.K;
-    const int npipes = c.nwc / T;
-    const bool active = c.warp < npipes * T;
-    const int pl = c.warp / T, stage = c.warp - pl * T;
-    const int half_id = c.lane >> 4, j = c.lane & 15, swap = (j >> 2) & 1;
-    const bool dual = (op.kind == OP_FFN);
-    const int colb = q4_col_bytes(K), G = q4_groups(K), zh = q4_zh(K);
-    // a thread whose two reference lanes lie beyond K (partial last trip) carries the accumulator through
-    const bool lanes_live = active && (stage * 1024 + j * 64 < K);
-
-    // ---- activation slice -> registers: xp[m] = (x[k0 + m], x[k1 + m]), k0/k1 = first k of the two owned lanes ----
-    unsigned long long xp[32];
-    {
-        const half* xin = op.x;
-        if (op.emb != nullptr) {
-            const int token = op.tokens[c.pos];
-            xin = op.emb + (size_t)token * K;
-            if (blockIdx.x == 0 && op.x_copy != nullptr)
-                for (int k = c.ctid; k < K; k += c.nthreads) op.x_copy[k] = xin[k];
+// Scales and zero points of the columns this CTA owns in the current op -> shared memory.
+//   GEMV: [scales: ncol x G halfs][zeros: ncol x zh words], columns in concatenated (q|k|v) order
+//   FFN : [gate scales][up scales][gate zeros][up zeros], nout outputs each
+// Returns the byte offset of the zero-point block (GEMV) / of one block to the next (FFN uses the same helper).
+__device__ void stage_meta(Ctx& c, const Op& op, int t0, int t1) {
+    const int G = q4_groups(op.K), zh = q4_zh(op.K);
+    if (op.kind == OP_FFN) {
+        const int o0 = t0 * 2, nout = (t1 - t0) * 2;
+        const int sw = nout * G / 2, zw = nout * zh;          // words per block (nout even: G*nout/2 is whole)
+        for (int m = 0; m < 2; m++) {
+            copy_words(c, c.sm.meta + (m * sw) * 4, reinterpret_cast<const uint32_t*>(op.seg[m].s + (size_t)o0 * G), sw);
+            copy_words(c, c.sm.meta + (2 * sw + m * zw) * 4, op.seg[m].z + (size_t)o0 * zh, zw);
         }
-        const bool norm = (op.norm_w != nullptr);
-        // slot 0 = reference lane 2j+swap, slot 1 = reference lane 2j+1-swap (see q4_step)
-        const int k0 = stage * 1024 + j * 64 + (swap ? 32 : 0), k1 = stage * 1024 + j * 64 + (swap ? 0 : 32);
-        uint4 r0[4], r1[4], n0[4], n1[4];
-        if (lanes_live) {
-#pragma unroll
-            for (int v = 0; v < 4; v++) { r0[v] = ld_cg_v4(xin + k0 + v * 8); r1[v] = ld_cg_v4(xin + k1 + v * 8); }
-            if (norm) {
-#pragma unroll
-                for (int v = 0; v < 4; v++) { n0[v] = ldg_stream_v4(op.norm_w + k0 + v * 8); n1[v] = ldg_stream_v4(op.norm_w + k1 + v * 8); }
-            }
-        }
-        float scale = 1.0f;
-        if (norm) scale = cta_rms_scale(c, xin, K);
-        if (lanes_live) {
-#pragma unroll
-            for (int m = 0; m < 32; m++) {
-                const int wi = m >> 1;   // 32-bit word holding element m
-                const uint32_t a0 = (wi & 3) == 0 ? r0[wi >> 2].x : (wi & 3) == 1 ? r0[wi >> 2].y : (wi & 3) == 2 ? r0[wi >> 2].z : r0[wi >> 2].w;
-                const uint32_t a1 = (wi & 3) == 0 ? r1[wi >> 2].x : (wi & 3) == 1 ? r1[wi >> 2].y : (wi & 3) == 2 ? r1[wi >> 2].z : r1[wi >> 2].w;
-                const uint32_t h0 = (m & 1) ? (a0 >> 16) : (a0 & 0xFFFFu), h1 = (m & 1) ? (a1 >> 16) : (a1 & 0xFFFFu);
-                uint32_t g0 = 0, g1 = 0;
-                if (norm) {
-                    const uint32_t b0 = (wi & 3) == 0 ? n0[wi >> 2].x : (wi & 3) == 1 ? n0[wi >> 2].y : (wi & 3) == 2 ? n0[wi >> 2].z : n0[wi >> 2].w;
-                    const uint32_t b1 = (wi & 3) == 0 ? n1[wi >> 2].x : (wi & 3) == 1 ? n1[wi >> 2].y : (wi & 3) == 2 ? n1[wi >> 2].z : n1[wi >> 2].w;
-                    g0 = (m & 1) ? (b0 >> 16) : (b0 & 0xFFFFu);
-                    g1 = (m & 1) ? (b1 >> 16) : (b1 & 0xFFFFu);
-                }
-                xp[m] = pack_f2(h2f_bits(norm_h(h0, g0, scale, norm)), h2f_bits(norm_h(h1, g1, scale, norm)));
-            }
-        } else {
-#pragma unroll
-            for (int m = 0; m < 32; m++) xp[m] = 0ull;
+    } else {
+        const int c0 = t0 * 4, ncol = (t1 - t0) * 4;
+        const int zoff = ncol * G * 2;
+        int done = 0;
+        while (done < ncol) {                                 // one piece per matrix the range touches
+            int seg, col;
+            gemv_locate(op, c0 + done, seg, col);
+            int n = op.seg[seg].ncols - col;
+            if (n > ncol - done) n = ncol - done;
+            copy_words(c, c.sm.meta + done * G * 2, reinterpret_cast<const uint32_t*>(op.seg[seg].s + (size_t)col * G), n * G / 2);
+            copy_words(c, c.sm.meta + zoff + done * zh * 4, op.seg[seg].z + (size_t)col * zh, n * zh);
+            done += n;
         }
     }
+}
 
-    // ---- stream this CTA's chunks ----
-    int c0, c1;
-    cta_range(op, blockIdx.x, gridDim.x, c0, c1);
-    float2* hand_in = c.hand + (size_t)(c.warp - 1) * 64;   // written by stage-1 (only read when stage > 0)
-    float2* hand_out = c.hand + (size_t)c.warp * 64;
-    const int pipe_threads = T * 32;
-    const int bar_id = 1 + pl;
-    int step = stage;                 // lock-step counter of this pipeline
-    if (active && T > 1)
-        for (int s = 0; s < stage; s++) named_bar(bar_id, pipe_threads);   // fill skew
-    int pair_base = 0;                // pairs of this CTA's range before the current chunk
-    for (int cc = c0; cc < c1;) {
-        const Chunk ch = next_chunk(op, cc, c1);
-        const unsigned slot = c.seq % c.P->nslots, use = c.seq / c.P->nslots;
-        mbar_wait(c.full0 + 8 * slot, use & 1);
-        const int npairs = dual ? ch.n : (ch.n >> 1);
-        if (active) {
-            const int nm = dual ? 2 : 1;
-            const uint32_t base = smem_u32(c.ring + (size_t)slot * c.P->slot_bytes);
-            const uint32_t wb = (uint32_t)ch.n * colb, sb = (uint32_t)ch.n * G * 2, zb = (uint32_t)ch.n * zh * 4;
-            const Seg& sg = op.seg[dual ? 0 : ch.seg];
-            // first pair of this chunk owned by my pipeline: global pair index q = pl (mod npipes)
-            int p = (pl - pair_base % npipes + npipes) % npipes;
-            for (; p < npairs; p += npipes) {
-                const int lcol = dual ? p : 2 * p + half_id;          // column inside the chunk
-                const int m = dual ? half_id : 0;                      // matrix (gate / up)
-                const uint32_t wcol = base + m * wb + (uint32_t)lcol * colb;
-                const uint32_t scol = base + nm * wb + m * sb + (uint32_t)lcol * G * 2;
-                const uint32_t zcol = base + nm * (wb + sb) + m * zb + (uint32_t)lcol * zh * 4;
-                unsigned long long acc = 0ull;
-                if (stage > 0) {
-                    const float2 in = hand_in[((step - 1) & 1) * 32 + c.lane];
-                    acc = pack_f2(in.x, in.y);
-                }
-                if (lanes_live) q4_step(acc, xp, wcol, scol, zcol, stage, j, swap);
-                if (stage == T - 1) {
-                    // cub::WarpReduce order over the 32 reference lanes (shfl_down 1,2,4,8,16): the first level
-                    // pairs lanes (2j, 2j+1) = this thread's two chains, the rest is a butterfly over 16 threads
-                    float a0, a1;
-                    unpack_f2(acc, a0, a1);
-                    float v = a0 + a1;
-                    v = v + __shfl_xor_sync(0xffffffffu, v, 1);
-                    v = v + __shfl_xor_sync(0xffffffffu, v, 2);
-                    v = v + __shfl_xor_sync(0xffffffffu, v, 4);
-                    v = v + __shfl_xor_sync(0xffffffffu, v, 8);
-                    if (dual) {
-                        const float u = __shfl_sync(0xffffffffu, v, 16);
-                        if (c.lane == 0) {   // gpu_kernels.h:269-273
-                            float val = v;
-                            val = __fmul_rn(val, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-val))));
-                            val = __fmul_rn(val, u);
-                            sg.out[ch.col + p] = __float2half_rn(val);
-                        }
-                    } else if (j == 0) {
-                        half* dst = sg.out;
-                        if (sg.pos_stride != 0) dst += sg.loff + (size_t)c.pos * sg.pos_stride;
-                        const int col = ch.col + lcol;
-                        float sum = v;
-                        if (op.accum) sum = sum + h2f_bits(ld_cg_u16(dst + col));
-                        dst[col] = __float2half_rn(sum);
-                    }
-                } else {
-                    float a0, a1;
-                    unpack_f2(acc, a0, a1);
-                    hand_out[(step & 1) * 32 + c.lane] = make_float2(a0, a1);
-                }
-                if (T > 1) named_bar(bar_id, pipe_threads);
-                step++;
+// ------------------------------------------------------------------------------------------------
+// Activation staging for the INT4 ops: x (fp16, global) -> fp32 PAIRS in shared memory.
+// Thread (half-warp lane j) of a consumer warp owns reference lanes A = 2j + sw and B = 2j + 1 - sw, sw = (j>>2)&1
+// (the swap keeps its two 16-byte weight loads bank-conflict free).  Pair (trip t, j, i) = (x[t*1024 + A*32 + i],
+// x[t*1024 + B*32 + i]) lives at byte  t*4096 + (i>>1)*256 + j*16 + (i&1)*8, so that one 16-byte load per thread
+// fetches two pairs and the 16 threads of a half-warp read 256 contiguous bytes.
+// ------------------------------------------------------------------------------------------------
+__device__ void stage_x_pairs(Ctx& c, const Op& op, int t0, int t1) {
+    const int K = op.K;
+    const half* xin = op.x;
+    named_bar(kBarAll, c.nthreads);   // every warp is done reading the previous op's staging areas
+    stage_meta(c, op, t0, t1);
+    if (op.emb != nullptr) {
+        const int token = op.tokens[c.pos];
+        xin = op.emb + (size_t)token * K;
+        if (blockIdx.x == 0 && op.x_copy != nullptr)
+            for (int k = c.ctid; k < K; k += c.nthreads) op.x_copy[k] = xin[k];
+    }
+    const bool norm = (op.norm_w != nullptr);
+    float scale = 1.0f;
+    if (norm) scale = cta_rms_scale(c, xin, K);
+    const int units = op.T * 64;      // (t, i8, j): 8 pairs each
+    for (int u = c.ctid; u < units; u += c.nthreads) {
+        const int t = u >> 6, i8 = (u >> 4) & 3, j = u & 15, sw = (j >> 2) & 1;
+        const int k0 = t * 1024 + (2 * j + sw) * 32 + i8 * 8, k1 = t * 1024 + (2 * j + 1 - sw) * 32 + i8 * 8;
+        if (k0 >= K) continue;        // K % 64 == 0: both lanes of a thread are live or dead together
+        const uint4 r0 = ld_cg_v4(xin + k0), r1 = ld_cg_v4(xin + k1);
+        uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+        if (norm) { n0 = ldg_stream_v4(op.norm_w + k0); n1 = ldg_stream_v4(op.norm_w + k1); }
+        const uint32_t dst = c.sm.xs + t * 4096 + (i8 * 4) * 256 + j * 16;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {      // word q holds elements 2q, 2q+1
+            const uint32_t a = word_of(r0, q), b = word_of(r1, q), na = word_of(n0, q), nb = word_of(n1, q);
+            const float a0 = h2f_bits(norm_h(a & 0xFFFFu, na & 0xFFFFu, scale, norm)), a1 = h2f_bits(norm_h(a >> 16, na >> 16, scale, norm));
+            const float b0 = h2f_bits(norm_h(b & 0xFFFFu, nb & 0xFFFFu, scale, norm)), b1 = h2f_bits(norm_h(b >> 16, nb >> 16, scale, norm));
+            sts_v4(dst + q * 256, a0, b0, a1, b1);
+        }
+    }
+    named_bar(kBarAll, c.nthreads);
+}
+
+// ------------------------------------------------------------------------------------------------
+// INT4 GEMV / FFN consumer.  One trip of one warp-task: every thread advances the two lane chains of its two
+// columns by 32 k each (128 weights).  acc.lo = chain of reference lane A, acc.hi = chain of lane B.
+// ------------------------------------------------------------------------------------------------
+struct ColMeta {
+    uint32_t s16;      // fp16 scale bits of this trip's group
+    float nlo, nhi;    // -(1024+z)*s and -(64+z)*s, exact
+};
+__device__ __forceinline__ ColMeta col_meta(uint32_t scol, uint32_t zcol, int t, int j) {
+    ColMeta m;
+    m.s16 = lds_u16(scol + (t * 8 + (j >> 1)) * 2);
+    const uint32_t zw = lds_u32(zcol + t * 4);
+    const uint32_t zp = ((zw >> ((j >> 1) * 4)) & 0xFu) | 0x6400u;             // fp16 bits of 1024 + z
+    m.nlo = fhfma_lo(zp, m.s16 ^ 0x8000u, 0.0f);                               // -(1024+z)*s, exact
+    m.nhi = fhfma_lo(0x6380u, m.s16, m.nlo);                                   // -(64+z)*s = 960*s + nlo, exact
+    return m;
+}
+
+__device__ __forceinline__ void q4_trip2(unsigned long long& acc0, unsigned long long& acc1, uint32_t xaddr, uint32_t w0, uint32_t w1,
+                                         const ColMeta& m0, const ColMeta& m1) {
+    const uint4 wa0 = lds_v4(w0), wb0 = lds_v4(w0 ^ 16), wa1 = lds_v4(w1), wb1 = lds_v4(w1 ^ 16);
+#pragma unroll
+    for (int qi = 0; qi < 4; qi++) {
+        float da0[8], db0[8], da1[8], db1[8];
+        dequant8(da0, word_of(wa0, qi), m0.s16, m0.nlo, m0.nhi);
+        dequant8(db0, word_of(wb0, qi), m0.s16, m0.nlo, m0.nhi);
+        dequant8(da1, word_of(wa1, qi), m1.s16, m1.nlo, m1.nhi);
+        dequant8(db1, word_of(wb1, qi), m1.s16, m1.nlo, m1.nhi);
+#pragma unroll
+        for (int e2 = 0; e2 < 4; e2++) {
+            unsigned long long xp0, xp1;
+            lds_v2_b64(xaddr + (qi * 4 + e2) * 256, xp0, xp1);
+            ffma2_pk(acc0, da0[2 * e2], db0[2 * e2], xp0);
+            ffma2_pk(acc1, da1[2 * e2], db1[2 * e2], xp0);
+            ffma2_pk(acc0, da0[2 * e2 + 1], db0[2 * e2 + 1], xp1);
+            ffma2_pk(acc1, da1[2 * e2 + 1], db1[2 * e2 + 1], xp1);
+        }
+    }
+}
+
+// cub::WarpReduce order over the 32 reference lanes of a column held by a half-warp: level 1 pairs lanes
+// (2j, 2j+1) = this thread's two chains, levels 2..5 are a butterfly over the 16 threads.
+__device__ __forceinline__ float halfwarp_total(unsigned long long acc) {
+    float a0, a1;
+    unpack_f2(acc, a0, a1);
+    float v = a0 + a1;
+    v = v + __shfl_xor_sync(0xffffffffu, v, 1);
+    v = v + __shfl_xor_sync(0xffffffffu, v, 2);
+    v = v + __shfl_xor_sync(0xffffffffu, v, 4);
+    v = v + __shfl_xor_sync(0xffffffffu, v, 8);
+    return v;
+}
+
+// first ring slot / phase of a task, and stepping to the next slot
+struct RingPos {
+    int slot;
+    unsigned lap;
+};
+__device__ __forceinline__ RingPos ring_pos(const Ctx& c, unsigned q) {
+    RingPos r;
+    r.lap = q / (unsigned)c.sm.S;
+    r.slot = (int)(q - r.lap * c.sm.S);
+    return r;
+}
+__device__ __forceinline__ void ring_next(const Ctx& c, RingPos& r) {
+    if (++r.slot == c.sm.S) { r.slot = 0; r.lap++; }
+}
+// Wait until chunk (slot, lap) has landed.  A parity wait cannot tell lap L from lap L-2, and a warp may be several
+// laps ahead of the ring (tasks are dealt round-robin), so first wait until the slot has been released `lap` times:
+// from then on the only phase of its full barrier that can still complete is this chunk's.
+__device__ __forceinline__ void ring_wait(const Ctx& c, const RingPos& r) {
+    unsigned done;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(done) : "r"(c.sm.laps + r.slot * 4) : "memory");
+    if (done < r.lap) {
+        const unsigned long long t0 = global_ns();
+        do {
+            asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(done) : "r"(c.sm.laps + r.slot * 4) : "memory");
+            if (global_ns() - t0 > kWaitLimitNs) asm volatile("trap;");
+        } while (done < r.lap);
+    }
+    mbar_wait(c.sm.full(r.slot), r.lap & 1);
+}
+// lane 0 of the consuming warp, after the whole warp is done with the slot
+__device__ __forceinline__ void ring_release(const Ctx& c, const RingPos& r) {
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(c.sm.laps + r.slot * 4), "r"(r.lap + 1) : "memory");
+    mbar_arrive(c.sm.empty(r.slot));
+}
+
+__device__ void run_q4(Ctx& c, const Op& op) {
+    int t0, t1;
+    cta_task_range(op, blockIdx.x, gridDim.x, t0, t1);
+    stage_x_pairs(c, op, t0, t1);
+    const int K = op.K, T = op.T, G = q4_groups(K), zh = q4_zh(K), colb = q4_col_bytes(K);
+    const int cps = op.cps, spt = op.spt;
+    const bool dual = (op.kind == OP_FFN);
+    const int h = c.lane >> 4, j = c.lane & 15, sw = (j >> 2) & 1;
+    for (int task = t0 + c.warp; task < t1; task += c.nwc) {
+        // ---- my two columns: where their weights, scales and zeros are ----
+        RingPos rp = ring_pos(c, c.qbase + (unsigned)(task - t0) * spt);
+        int seg = 0, col = 0;
+        uint32_t scol0, scol1, zcol0, zcol1, w0, w1;
+        // wait for every slot of the task
+        {
+            RingPos r = rp;
+            for (int i = 0; i < spt; i++) { ring_wait(c, r); ring_next(c, r); }
+        }
+        if (dual) {
+            const int nout = (t1 - t0) * 2, lo = (task - t0) * 2 + h;      // local output index
+            col = task * 2 + h;
+            scol0 = c.sm.meta + lo * G * 2;                         scol1 = scol0 + nout * G * 2;
+            zcol0 = c.sm.meta + 2 * nout * G * 2 + lo * zh * 4;     zcol1 = zcol0 + nout * zh * 4;
+            // slot: [gate cps columns][up cps columns]; output h of the task is column h % cps of slot h / cps
+            RingPos r = rp;
+            if (h >= cps) ring_next(c, r);                            // cps == 1: second output sits in the second slot
+            w0 = c.sm.slot(r.slot) + (h % cps) * colb;
+            w1 = w0 + cps * colb;
+        } else {
+            const int ncol = (t1 - t0) * 4, lc = (task - t0) * 4 + 2 * h;  // local index of my first column
+            gemv_locate(op, task * 4, seg, col);
+            col += 2 * h;
+            scol0 = c.sm.meta + lc * G * 2;                         scol1 = scol0 + G * 2;
+            zcol0 = c.sm.meta + ncol * G * 2 + lc * zh * 4;         zcol1 = zcol0 + zh * 4;
+            // column i (0..3) of the task is column i % cps of slot i / cps
+            RingPos r = rp;
+            const int i0 = 2 * h, i1 = 2 * h + 1;
+            for (int s = 0; s < i0 / cps; s++) ring_next(c, r);
+            w0 = c.sm.slot(r.slot) + (i0 % cps) * colb;
+            if (i1 / cps != i0 / cps) ring_next(c, r);
+            w1 = c.sm.slot(r.slot) + (i1 % cps) * colb;
+        }
+        w0 += j * 32 + sw * 16;
+        w1 += j * 32 + sw * 16;
+        unsigned long long acc0 = 0ull, acc1 = 0ull;
+        const int tlive = (K - j * 64 + 1023) >> 10;      // trips in which this thread's lanes hold data
+        for (int t = 0; t < T; t++) {
+            if (t < tlive) {
+                const ColMeta m0 = col_meta(scol0, zcol0, t, j), m1 = col_meta(scol1, zcol1, t, j);
+                q4_trip2(acc0, acc1, c.sm.xs + t * 4096 + j * 16, w0 + t * 512, w1 + t * 512, m0, m1);
             }
         }
         __syncwarp();
-        if (c.lane == 0) mbar_arrive(c.empty0 + 8 * slot);
-        pair_base += npairs;
-        c.seq++;
-        cc += ch.n;
+        if (c.lane == 0) {
+            RingPos r = rp;
+            for (int i = 0; i < spt; i++) { ring_release(c, r); ring_next(c, r); }
+        }
+        // ---- epilogue ----
+        const float v0 = halfwarp_total(acc0), v1 = halfwarp_total(acc1);
+        if (j == 0) {
+            if (dual) {                                          // gpu_kernels.h:269-273
+                float val = v0;
+                val = __fmul_rn(val, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-val))));
+                val = __fmul_rn(val, v1);
+                op.seg[0].out[col] = __float2half_rn(val);
+            } else {
+                const Seg& sg = op.seg[seg];
+                half* dst = sg.out;
+                if (sg.pos_stride != 0) dst += sg.loff + (size_t)c.pos * sg.pos_stride;
+                float s0 = v0, s1 = v1;
+                if (op.accum) {
+                    s0 = s0 + h2f_bits(ld_cg_u16(dst + col));
+                    s1 = s1 + h2f_bits(ld_cg_u16(dst + col + 1));
+                }
+                dst[col] = __float2half_rn(s0);
+                dst[col + 1] = __float2half_rn(s1);
+            }
+        }
     }
-    if (active && T > 1)
-        for (int s = 0; s < T - 1 - stage; s++) named_bar(bar_id, pipe_threads);   // drain skew
+    c.qbase += (unsigned)(t1 - t0) * spt;
 }
 
 // ------------------------------------------------------------------------------------------------
 // fp16 classifier consumer (mat_vec_kernel, gpu_kernels.h:109-139).  Reference lane L chains
-// k = (trip*32 + L)*8 + el over trips; stage i of a pipeline owns trips 4i..4i+3 (1024 k).  One thread is
-// one reference lane, a warp step is two rows.
+// k = (trip*32 + L)*8 + el over trips of 256 k; one thread is one reference lane of four rows.
 // ------------------------------------------------------------------------------------------------
 __device__ void run_cls(Ctx& c, const Op& op) {
-    const int T = op.T, n = op.K;
-    const int npipes = c.nwc / T;
-    const bool active = c.warp < npipes * T;
-    const int pl = c.warp / T, stage = c.warp - pl * T;
-    const int lane = c.lane;
-
-    uint4 xh[4];   // 8 halves per trip
+    const int n = op.K, T = op.T, lane = c.lane, cps = op.cps, spt = op.spt;
+    // ---- stage x as fp16 (through the fused RMSNorm) ----
+    named_bar(kBarAll, c.nthreads);
     {
         const bool norm = (op.norm_w != nullptr);
-        uint4 wn[4];
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-            const int jx = ((stage * 4 + t) * 32 + lane) * 8;
-            xh[t] = make_uint4(0, 0, 0, 0);
-            wn[t] = make_uint4(0, 0, 0, 0);
-            if (active && jx < n) {
-                xh[t] = ld_cg_v4(op.x + jx);
-                if (norm) wn[t] = ldg_stream_v4(op.norm_w + jx);
-            }
-        }
-        if (norm) {
-            const float scale = cta_rms_scale(c, op.x, n);
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                uint32_t* xv = &xh[t].x;
-                const uint32_t* wv = &wn[t].x;
+        float scale = 1.0f;
+        if (norm) scale = cta_rms_scale(c, op.x, n);
+        for (int u = c.ctid; u * 8 < n; u += c.nthreads) {
+            uint4 xv = ld_cg_v4(op.x + u * 8);
+            if (norm) {
+                const uint4 wv = ldg_stream_v4(op.norm_w + u * 8);
+                uint32_t* xw = &xv.x;
+                const uint32_t* ww = &wv.x;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    const uint32_t lo = norm_h(xv[q] & 0xFFFFu, wv[q] & 0xFFFFu, scale, true);
-                    const uint32_t hi = norm_h(xv[q] >> 16, wv[q] >> 16, scale, true);
-                    xv[q] = lo | (hi << 16);
+                    const uint32_t lo = norm_h(xw[q] & 0xFFFFu, ww[q] & 0xFFFFu, scale, true);
+                    const uint32_t hi = norm_h(xw[q] >> 16, ww[q] >> 16, scale, true);
+                    xw[q] = lo | (hi << 16);
                 }
             }
+            sts_v4_u32(c.sm.xs + u * 16, xv);
         }
     }
+    named_bar(kBarAll, c.nthreads);
 
-    int c0, c1;
-    cta_range(op, blockIdx.x, gridDim.x, c0, c1);
-    float2* hand_in = c.hand + (size_t)(c.warp - 1) * 64;
-    float2* hand_out = c.hand + (size_t)c.warp * 64;
-    const int pipe_threads = T * 32, bar_id = 1 + pl;
-    int step = stage;
-    if (active && T > 1)
-        for (int s = 0; s < stage; s++) named_bar(bar_id, pipe_threads);
-    int pair_base = 0;
-    for (int cc = c0; cc < c1;) {
-        const Chunk ch = next_chunk(op, cc, c1);
-        const unsigned slot = c.seq % c.P->nslots, use = c.seq / c.P->nslots;
-        mbar_wait(c.full0 + 8 * slot, use & 1);
-        const int npairs = (ch.n + 1) >> 1;
-        if (active) {
-            const uint32_t base = smem_u32(c.ring + (size_t)slot * c.P->slot_bytes);
-            int p = (pl - pair_base % npipes + npipes) % npipes;
-            for (; p < npairs; p += npipes) {
-                float acc[2] = {0.0f, 0.0f};
-                if (stage > 0) {
-                    const float2 in = hand_in[((step - 1) & 1) * 32 + lane];
-                    acc[0] = in.x; acc[1] = in.y;
-                }
+    int t0, t1;
+    cta_task_range(op, blockIdx.x, gridDim.x, t0, t1);
+    for (int task = t0 + c.warp; task < t1; task += c.nwc) {
+        int rows = op.seg[0].ncols - task * 4;
+        if (rows > 4) rows = 4;
+        const RingPos rp = ring_pos(c, c.qbase + (unsigned)(task - t0) * spt);
+        uint32_t wrow[4];
+        {
+            RingPos r = rp;
+            for (int i = 0; i < spt; i++) {
+                ring_wait(c, r);
 #pragma unroll
-                for (int r = 0; r < 2; r++) {
-                    const int lrow = 2 * p + r;
-                    if (lrow < ch.n) {
-                        const uint32_t row = base + (uint32_t)lrow * n * 2;
+                for (int q = 0; q < 4; q++)
+                    if (q / cps == i) wrow[q] = c.sm.slot(r.slot) + (q % cps) * n * 2 + lane * 16;
+                ring_next(c, r);
+            }
+        }
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        for (int t = 0; t < T; t++) {
+            const int jx = (t * 32 + lane) * 8;
+            if (jx < n) {
+                const uint4 xv = lds_v4(c.sm.xs + jx * 2);
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    if (r < rows) {
+                        const uint4 w = lds_v4(wrow[r] + t * 512);
                         float a = acc[r];
-#pragma unroll
-                        for (int t = 0; t < 4; t++) {
-                            const int jx = ((stage * 4 + t) * 32 + lane) * 8;
-                            if (jx < n) {
-                                const uint4 w = lds_v4(row + jx * 2);
-                                const uint4 xv = xh[t];
-                                a = fhfma_ll(w.x, xv.x, a); a = fhfma_hh(w.x, xv.x, a);
-                                a = fhfma_ll(w.y, xv.y, a); a = fhfma_hh(w.y, xv.y, a);
-                                a = fhfma_ll(w.z, xv.z, a); a = fhfma_hh(w.z, xv.z, a);
-                                a = fhfma_ll(w.w, xv.w, a); a = fhfma_hh(w.w, xv.w, a);
-                            }
-                        }
+                        a = fhfma_ll(w.x, xv.x, a); a = fhfma_hh(w.x, xv.x, a);
+                        a = fhfma_ll(w.y, xv.y, a); a = fhfma_hh(w.y, xv.y, a);
+                        a = fhfma_ll(w.z, xv.z, a); a = fhfma_hh(w.z, xv.z, a);
+                        a = fhfma_ll(w.w, xv.w, a); a = fhfma_hh(w.w, xv.w, a);
                         acc[r] = a;
                     }
                 }
-                if (stage == T - 1) {
-#pragma unroll
-                    for (int r = 0; r < 2; r++) {
-                        const float tot = warp_tree_sum(acc[r]);
-                        const int lrow = 2 * p + r;
-                        if (lane == 0 && lrow < ch.n)
-                            op.seg[0].out[ch.col + lrow] = __float2half_rn(__fmul_rn(tot, op.alpha));
-                    }
-                } else {
-                    hand_out[(step & 1) * 32 + lane] = make_float2(acc[0], acc[1]);
-                }
-                if (T > 1) named_bar(bar_id, pipe_threads);
-                step++;
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(c.empty0 + 8 * slot);
-        pair_base += npairs;
-        c.seq++;
-        cc += ch.n;
+        if (lane == 0) {
+            RingPos r = rp;
+            for (int i = 0; i < spt; i++) { ring_release(c, r); ring_next(c, r); }
+        }
+        const float tot = warp_tree_sum4(acc[0], acc[1], acc[2], acc[3], lane);   // lanes 0,1,2,3 hold rows 0,2,1,3
+        if (lane < 4) {
+            const int r = 2 * (lane & 1) + ((lane >> 1) & 1);
+            if (r < rows) op.seg[0].out[task * 4 + r] = __float2half_rn(__fmul_rn(tot, op.alpha));
+        }
     }
-    if (active && T > 1)
-        for (int s = 0; s < T - 1 - stage; s++) named_bar(bar_id, pipe_threads);
+    c.qbase += (unsigned)(t1 - t0) * spt;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -775,7 +866,6 @@ __device__ void run_argmax(Ctx& c, const Op& op, int write_token) {
     }
     named_bar(kBarAll, c.nthreads);
 }
-
 // ------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------
@@ -783,17 +873,20 @@ __global__ void __launch_bounds__(512, 1) interp_kernel(const __grid_constant__ 
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const Op* ops = (P.ops != nullptr) ? P.ops : &P.one;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);                 // full[nslots], empty[nslots]
-    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * P.nslots;
-    float* red = reinterpret_cast<float*>(smem + 512);                   // 64 floats
-    float2* hand = reinterpret_cast<float2*>(smem + kCtrlBytes);
-    uint8_t* scratch = smem + kCtrlBytes + P.nwc * kHandBytes;
-    uint8_t* ring = scratch + P.scratch_bytes;
+    Smem sm;
+    sm.S = P.nslots;
+    sm.slot_bytes = P.slot_bytes;
+    sm.bars = smem_u32(smem);
+    sm.laps = sm.bars + kLapOffset;
+    sm.xs = sm.bars + kCtrlBytes;
+    sm.meta = sm.xs + P.xs_bytes;
+    sm.ring = sm.meta + P.meta_bytes;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.nslots; s++) {
-            mbar_init(full0 + 8 * s, 1);
-            mbar_init(empty0 + 8 * s, P.nwc);
+            mbar_init(sm.full(s), 1);
+            mbar_init(sm.empty(s), 1);
+            reinterpret_cast<volatile unsigned*>(smem + kLapOffset)[s] = 0u;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -801,15 +894,17 @@ __global__ void __launch_bounds__(512, 1) interp_kernel(const __grid_constant__ 
     __syncthreads();
 
     if (warp == P.nwc) {
-        if (lane == 0) producer_loop(P, ops, ring, full0, empty0);
+        if (lane == 0) producer_loop(P, ops, sm);
         return;
     }
 
     Ctx c;
-    c.P = &P; c.ring = ring; c.full0 = full0; c.empty0 = empty0; c.red = red; c.hand = hand; c.scratch = scratch;
+    c.P = &P; c.sm = sm;
+    c.red = reinterpret_cast<float*>(smem + kRedOffset);
+    c.scratch = smem + kCtrlBytes;
     c.nwc = P.nwc; c.nthreads = P.nwc * 32; c.warp = warp; c.lane = lane; c.ctid = threadIdx.x;
     c.pos = (P.pPos != nullptr) ? *P.pPos : 0;
-    c.seq = 0; c.nsync = 0;
+    c.qbase = 0; c.nsync = 0;
 
     for (int o = 0; o < P.nops; o++) {
         const Op& op = ops[o];
