@@ -96,6 +96,9 @@ const char* lq4_last_error(void);
 int lq4_sm_count(void);
 void lq4_set_option(const char* name, int value); /* "pdl" (0/1), "fused" (0/1), "graphs" (0/1) */
 
+/* development aid: per-op timestamps (ns) of the last fused step after lq4_set_option("trace", 1) */
+int lq4_debug_trace(unsigned long long* out, int* kinds, int max);
+
 /* ---- operator API ---- */
 /* rmsnorm, llama2_q4.cu:209-212 -> rmsnorm_kernel gpu_kernels.h:72-105 */
 void lq4_rmsnorm(lq4_half* o, lq4_half* x, lq4_half* weight, int size);

@@ -14,7 +14,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libllama_q4_b200.so")
+LIB_PATH = os.environ.get("LQ4_LIB") or os.path.join(_HERE, "libllama_q4_b200.so")   # LQ4_LIB: development A/B builds only
 CSRC = os.path.join(_HERE, "csrc")
 
 MAX_SEQ_LEN = 128 * 1024
@@ -75,6 +75,7 @@ _SIGNATURES = {
     "lq4_last_error": (C.c_char_p, []),
     "lq4_sm_count": (C.c_int, []),
     "lq4_set_option": (None, [C.c_char_p, C.c_int]),
+    "lq4_debug_trace": (C.c_int, [C.POINTER(C.c_ulonglong), C.POINTER(C.c_int), C.c_int]),
     "lq4_rmsnorm": (None, [_P, _P, _P, C.c_int]),
     "lq4_matmul_fp16": (None, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]),
     "lq4_matmul_q4": (None, [_P, _P, C.POINTER(QWeight), C.c_int, C.c_int, C.c_int, C.c_int, _P]),

@@ -65,6 +65,10 @@ struct Engine {
     std::map<RopeKey, float2*> rope_tabs;
     std::map<const void*, NetPlan> nets;
     unsigned* sync = nullptr;
+    int opt_trace = 0;      // record per-op timestamps of fused steps (development aid)
+    int opt_trace_op = -1;  // op whose phases are recorded per CTA
+    unsigned long long* trace = nullptr;
+    int trace_n = 0;
     std::map<const void*, void*> arenas;   // Transformer* -> device arena (loader)
     char err[512] = {0};
 };
@@ -198,7 +202,7 @@ bool make_plan(Plan& pl, int nwc, int xs, int meta, int slot) {
     pl.xs_bytes = (xs + 127) & ~127;
     pl.meta_bytes = (meta + 127) & ~127;
     pl.slot_bytes = std::max(128, (slot + 127) & ~127);
-    const int fixed = kCtrlBytes + pl.xs_bytes + pl.meta_bytes;
+    const int fixed = kCtrlBytes + pl.xs_bytes + 2 * pl.meta_bytes;
     const int ring = g.max_smem - fixed;
     if (ring <= 0) return false;
     int n = ring / pl.slot_bytes;
@@ -226,6 +230,11 @@ bool q4_op_shape(Op& op, int K, const int* ncols, int nseg, bool dual) {
     }
     if (dual && ncols[0] != ncols[1]) return false;
     op.ntasks = dual ? ncols[0] / 2 : total / 4;
+    // CTA ranges start on multiples of `au` tasks so that the scale / zero rows of a range are whole 16-byte units
+    const int G = q4_groups(K), zh = q4_zh(K);
+    if (dual) op.au = (G % 4 == 0 && zh % 2 == 0) ? 1 : (G % 2 == 0) ? 2 : 4;
+    else op.au = (G % 2 == 0) ? 1 : 2;
+    if (op.ntasks % op.au) return false;
     return true;
 }
 bool cls_op_shape(Op& op, int n, int d, int row_stride) {
@@ -235,6 +244,7 @@ bool cls_op_shape(Op& op, int n, int d, int row_stride) {
     op.nseg = 1;
     op.seg[0].ncols = d;
     op.ntasks = (d + 3) / 4;
+    op.au = 1;
     op.row_stride = row_stride;
     return true;
 }
@@ -255,10 +265,15 @@ bool op_set_chunking(Op& op, int slot) {
     op.spt = per / cps;
     return true;
 }
-int op_xs_bytes(const Op& op) { return op.kind == OP_CLS ? op.K * 2 : op.T * 4096; }
+// staging area: fp32 pairs (INT4 ops) or fp16 x (classifier), plus raw fp16 x and norm weights when RMSNorm is fused
+int op_xs_bytes(const Op& op) {
+    const int raw = op.norm_w != nullptr ? op.K * 4 : 0;
+    return (op.kind == OP_CLS ? ((op.K * 2 + 127) & ~127) : op.T * 4096) + raw;
+}
 int op_meta_bytes(const Op& op, int grid) {
     if (op.kind == OP_CLS) return 0;
-    const int maxtasks = (op.ntasks + grid - 1) / grid;
+    const int units = op.ntasks / op.au;
+    const int maxtasks = ((units + grid - 1) / grid) * op.au;
     const int cols = maxtasks * 4;                   // 4 columns, or 2 gate + 2 up columns, per task
     return cols * (q4_groups(op.K) * 2 + q4_zh(op.K) * 4) + 64;
 }
@@ -276,6 +291,12 @@ void launch_interp(const Plan& pl, const Op* d_ops, int nops, const Op* one, con
     P.nwc = pl.nwc; P.nslots = pl.nslots; P.slot_bytes = pl.slot_bytes; P.meta_bytes = pl.meta_bytes; P.xs_bytes = pl.xs_bytes;
     P.write_token = write_token;
     P.sync = g.sync; P.pPos = pPos;
+    if (g.opt_trace && d_ops != nullptr && nops + 1 <= 2048) {
+        if (!g.trace) { LQ4_CHECK(cudaMalloc((void**)&g.trace, 4096 * sizeof(unsigned long long))); LQ4_CHECK(cudaMemset(g.trace, 0, 4096 * sizeof(unsigned long long))); }
+        P.trace = g.trace;
+        P.trace_op = g.opt_trace_op;
+        g.trace_n = nops + 1;
+    }
     if (one) P.one = *one;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -358,7 +379,26 @@ void lq4_set_option(const char* name, int value) {
     else if (!strcmp(name, "nwc")) { g.opt_nwc = value; cudaStreamSynchronize(g.stream); drop_net_plans(); }
     else if (!strcmp(name, "slot_bytes")) { g.opt_slot_bytes = value; cudaStreamSynchronize(g.stream); drop_net_plans(); }
     else if (!strcmp(name, "nslots")) { g.opt_nslots = value; cudaStreamSynchronize(g.stream); drop_net_plans(); }
+    else if (!strcmp(name, "trace")) g.opt_trace = value;
+    else if (!strcmp(name, "trace_op")) g.opt_trace_op = value;
     else if (!strcmp(name, "graphs")) { /* the decode step is a single launch: nothing to capture */ }
+}
+
+// development aid: timestamps (ns) of the last fused step, one per op start plus the end; returns the count
+int lq4_debug_trace(unsigned long long* out, int* kinds, int max) {
+    ensure_init();
+    if (!g.trace || g.trace_n == 0) return 0;
+    cudaStreamSynchronize(g.stream);
+    const int n = std::min(max, g.trace_n);
+    cudaMemcpy(out, g.trace, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost);
+    if (max >= 4096) cudaMemcpy(out + 2048, g.trace + 2048, sizeof(unsigned long long) * 2048, cudaMemcpyDeviceToHost);
+    if (kinds && !g.nets.empty()) {
+        NetPlan& np = g.nets.begin()->second;
+        std::vector<Op> ops(np.nops);
+        cudaMemcpy(ops.data(), np.d_ops, sizeof(Op) * np.nops, cudaMemcpyDeviceToHost);
+        for (int i = 0; i < n && i < np.nops; i++) kinds[i] = ops[i].kind * 100000 + ops[i].K;
+    }
+    return n;
 }
 
 // ---------------------------------------------------------------------------------- operator API

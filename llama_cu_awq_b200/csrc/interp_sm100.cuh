@@ -61,6 +61,7 @@ struct Op {
     int T;                 // trips: ceil(K / 1024)  (OP_CLS: ceil(n / 256))
     int cps;               // columns (gate/up pairs, rows) per ring slot: 4, 2 or 1
     int spt;               // ring slots per warp-task
+    int au;                // CTA task ranges start on multiples of `au` tasks (16-byte alignment of the scale/zero copies)
     int ntasks;            // warp-tasks of the whole op (4 columns | 2 gate/up pairs | 4 rows each)
     int nseg;
     int accum;             // OP_GEMV: out = half(sum + float(out))  (residual, gpu_kernels.h:229-230)
@@ -94,28 +95,33 @@ struct Op {
     int write_token;
 };
 
+static_assert(sizeof(Op) <= 512 && sizeof(Op) % 4 == 0, "Op must fit its shared-memory copy");
+
 struct InterpParams {
     const Op* ops;         // device op table, or nullptr: use `one`
     int nops;
     int nwc;               // consumer warps per CTA (blockDim.x = 32 * (nwc + 1))
     int nslots;            // ring slots
     int slot_bytes;        // bytes per ring slot (multiple of 128)
-    int meta_bytes;        // scale/zero staging area
+    int meta_bytes;        // one scale/zero buffer (there are two)
     int xs_bytes;          // activation staging area (aliased with the attention scratch)
     int write_token;       // overrides Op::write_token of OP_ARGMAX when >= 0
     unsigned* sync;        // [2] grid barrier counter, exit counter (zero between launches)
     const int* pPos;       // device position
+    unsigned long long* trace;   // optional [nops + 1] timestamps (ns): CTA 0 at the start of each op, and at the end
+    int trace_op;                // op whose phases every CTA records at trace[2048 + cta * 8 + k]
     Op one;                // inline single op (operator API)
 };
 
 constexpr int kMaxConsumerWarps = 15;
-constexpr int kMaxSlots = 128;
+constexpr int kMaxSlots = 120;
 constexpr int kBarAll = 13;        // named barrier: all consumer warps
 constexpr int kCtrlBytes = 4096;   // mbarriers (first 2 KB) + reduction scratch (at 3 KB)
 constexpr int kRedOffset = 3072;
 constexpr unsigned kSpinLimit = 1u << 24;
 constexpr unsigned long long kWaitLimitNs = 2000000000ull;   // a wait longer than 2 s is a protocol bug: trap
-constexpr int kLapOffset = 2048;   // per-slot release counters
+constexpr int kLapOffset = 2048;   // per-slot release counters (up to 120 words)
+constexpr int kOpOffset = 2560;    // the current op, copied from the table (512 bytes)
 // ------------------------------------------------------------------------------------------------
 // PTX: mbarrier, bulk copy, named barriers, coherent loads
 // ------------------------------------------------------------------------------------------------
@@ -192,11 +198,24 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     return (uint32_t)r;
 }
 // (acc.lo, acc.hi) = (w0*x.lo + acc.lo, w1*x.hi + acc.hi): two single-rounding fmaf in one FFMA2
+#ifndef LQ4_USE_FFMA2
+#define LQ4_USE_FFMA2 1
+#endif
 __device__ __forceinline__ void ffma2_pk(unsigned long long& acc, float w0, float w1, unsigned long long x) {
+#if LQ4_USE_FFMA2
     asm("{ .reg .b64 rw;\n\t"
         "mov.b64 rw, {%1, %2};\n\t"
         "fma.rn.f32x2 %0, rw, %3, %0; }"
         : "+l"(acc) : "f"(w0), "f"(w1), "l"(x));
+#else
+    asm("{ .reg .f32 a0, a1, x0, x1;\n\t"
+        "mov.b64 {a0, a1}, %0;\n\t"
+        "mov.b64 {x0, x1}, %3;\n\t"
+        "fma.rn.f32 a0, %1, x0, a0;\n\t"
+        "fma.rn.f32 a1, %2, x1, a1;\n\t"
+        "mov.b64 %0, {a0, a1}; }"
+        : "+l"(acc) : "f"(w0), "f"(w1), "l"(x));
+#endif
 }
 __device__ __forceinline__ unsigned long long pack_f2(float lo, float hi) {
     unsigned long long r;
@@ -211,20 +230,21 @@ __device__ __forceinline__ void unpack_f2(unsigned long long v, float& lo, float
 // Grid barrier between dependent ops.  `target` = arrivals expected so far (ordinal * gridDim.x).
 // Called by all consumer threads of every CTA; the producer warp never takes part.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target, int nthreads, int ctid) {
-    named_bar(kBarAll, nthreads);                 // this CTA's stores are issued
-    if (ctid == 0) {
-        __threadfence();
-        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
-        unsigned v;
+// arrive: one thread, after the CTA's named barrier (which orders the other threads' stores before this release)
+__device__ __forceinline__ void grid_arrive(unsigned* counter) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
+}
+// wait: acquire polls by one thread; the named barrier that follows hands the ordering on to the CTA
+__device__ __forceinline__ void grid_wait(unsigned* counter, unsigned target) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    if (v < target) {
         const unsigned long long t0 = global_ns();
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
             if (v < target && global_ns() - t0 > kWaitLimitNs) asm volatile("trap;");
         } while (v < target);
-        __threadfence();
     }
-    named_bar(kBarAll, nthreads);
 }
 
 __device__ __forceinline__ void lds_v2_b64(uint32_t addr, unsigned long long& a, unsigned long long& b) {
@@ -246,8 +266,10 @@ __host__ __device__ __forceinline__ int q4_col_bytes(int K) { return K >> 1; }
 
 // CTA b of nb owns warp-tasks [t0, t1) of the op
 __device__ __forceinline__ void cta_task_range(const Op& op, int b, int nb, int& t0, int& t1) {
-    t0 = (int)(((long long)op.ntasks * b) / nb);
-    t1 = (int)(((long long)op.ntasks * (b + 1)) / nb);
+    const int au = op.au > 0 ? op.au : 1;
+    const long long units = op.ntasks / au;       // the host guarantees ntasks % au == 0
+    t0 = (int)((units * b) / nb) * au;
+    t1 = (int)((units * (b + 1)) / nb) * au;
 }
 // GEMV: column c of the concatenated column space -> (matrix, column inside it)
 __device__ __forceinline__ void gemv_locate(const Op& op, int c, int& seg, int& col) {
@@ -257,15 +279,19 @@ __device__ __forceinline__ void gemv_locate(const Op& op, int c, int& seg, int& 
 }
 
 struct Smem {            // shared-memory map (shared-window addresses)
-    uint32_t bars;       // full[S], empty[S]
+    uint32_t bars;       // full[S], empty[S], mfull[2], mempty[2]
     uint32_t laps;       // [S] releases of each slot so far (consumers only)
     uint32_t xs;         // activation staging / attention scratch
-    uint32_t meta;       // scales and zero points of this CTA's columns for the current op
+    uint32_t meta;       // [2][meta_bytes] scales and zero points of this CTA's columns, ping-pong per INT4 op
+    int meta_bytes;
     uint32_t ring;       // [S][slot_bytes]
     int S, slot_bytes;
     __device__ __forceinline__ uint32_t full(int s) const { return bars + (uint32_t)s * 8; }
     __device__ __forceinline__ uint32_t empty(int s) const { return bars + (uint32_t)(S + s) * 8; }
     __device__ __forceinline__ uint32_t slot(int s) const { return ring + (uint32_t)s * slot_bytes; }
+    __device__ __forceinline__ uint32_t mfull(int b) const { return bars + (uint32_t)(2 * S + b) * 8; }
+    __device__ __forceinline__ uint32_t mempty(int b) const { return bars + (uint32_t)(2 * S + 2 + b) * 8; }
+    __device__ __forceinline__ uint32_t mbuf(int b) const { return meta + (uint32_t)b * meta_bytes; }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -279,12 +305,48 @@ __device__ void producer_loop(const InterpParams& P, const Op* ops, const Smem& 
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
     int slot = 0;
     uint32_t phase = 0;
+    unsigned mcount = 0, issued = 0;
     for (int o = 0; o < P.nops; o++) {
-        const Op& op = ops[o];
-        if (op.kind > OP_CLS) continue;
+        if (ops[o].kind > OP_CLS) continue;
+        const Op op = ops[o];         // private copy: the fields are read once, not once per copy
         int t0, t1;
         cta_task_range(op, blockIdx.x, gridDim.x, t0, t1);
         const int cps = op.cps, spt = op.spt;
+
+        if (op.kind != OP_CLS) {      // scales and zero points of the CTA's columns (layout: see stage_meta_layout)
+            const int b = mcount & 1;
+            mbar_wait(sm.mempty(b), ((mcount >> 1) & 1) ^ 1);
+            const uint32_t dst = sm.mbuf(b), bar = sm.mfull(b);
+            const int G = q4_groups(op.K), zh = q4_zh(op.K);
+            if (t1 > t0) {
+                if (op.kind == OP_FFN) {
+                    const int o0 = t0 * 2, nout = (t1 - t0) * 2;
+                    const uint32_t sb = nout * G * 2, zb = nout * zh * 4;
+                    mbar_arrive_expect_tx(bar, 2 * (sb + zb));
+                    for (int m = 0; m < 2; m++) {
+                        bulk_g2s(dst + m * sb, op.seg[m].s + (size_t)o0 * G, sb, bar, policy);
+                        bulk_g2s(dst + 2 * sb + m * zb, op.seg[m].z + (size_t)o0 * zh, zb, bar, policy);
+                    }
+                } else {
+                    const int c0 = t0 * 4, ncol = (t1 - t0) * 4;
+                    const uint32_t zoff = ncol * G * 2;
+                    mbar_arrive_expect_tx(bar, (uint32_t)ncol * (G * 2 + zh * 4));
+                    int done = 0;
+                    while (done < ncol) {                                 // one piece per matrix the range touches
+                        int seg, col;
+                        gemv_locate(op, c0 + done, seg, col);
+                        int n = op.seg[seg].ncols - col;
+                        if (n > ncol - done) n = ncol - done;
+                        bulk_g2s(dst + done * G * 2, op.seg[seg].s + (size_t)col * G, n * G * 2, bar, policy);
+                        bulk_g2s(dst + zoff + done * zh * 4, op.seg[seg].z + (size_t)col * zh, n * zh * 4, bar, policy);
+                        done += n;
+                    }
+                }
+            } else {
+                mbar_arrive(bar);
+            }
+            mcount++;
+        }
         const size_t colb = (op.kind == OP_CLS) ? (size_t)op.K * 2 : (size_t)q4_col_bytes(op.K);
         for (int task = t0; task < t1; task++) {
             int seg = 0, col = 0;
@@ -316,8 +378,11 @@ __device__ void producer_loop(const InterpParams& P, const Op* ops, const Smem& 
                     }
                 }
                 if (++slot == sm.S) { slot = 0; phase ^= 1; }
+                issued++;
+                asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(sm.bars + 3584), "r"(issued) : "memory");
             }
         }
+
     }
 }
 
@@ -333,26 +398,38 @@ struct Ctx {
     int warp, lane, ctid;
     int pos;
     unsigned qbase;           // ring chunks of all ops before the current one (this CTA)
+    unsigned mcount;          // INT4 ops so far (scale/zero buffer = mcount & 1)
+    int meta_pending;         // scale/zero buffer to hand back to the producer once every warp has left the op, or -1
     unsigned nsync;           // grid barriers taken so far
+    unsigned long long* tr;   // detailed phase trace of the current op (this CTA's 8 entries) or nullptr
 };
+__device__ __forceinline__ void trace_mark(const Ctx& c, int k) {
+    if (c.tr != nullptr && c.lane == 0 && (c.warp == 0 || k >= 8)) c.tr[k & 7] = global_ns();
+}
 
 // RMSNorm scale 1/sqrt(mean(x^2)+eps) in the reference's association (gpu_kernels.h:73-96): virtual
 // thread vt (of 1024) chains x[vt + 1024 i]^2, virtual warps are tree-summed, thread 0 adds the 32 warp
-// aggregates in order.  All consumer threads call this; returns the scale in every thread.
-__device__ float cta_rms_scale(Ctx& c, const half* x, int size) {
+// aggregates in order.  x is the raw fp16 vector already in shared memory.  All consumer threads call this;
+// returns the scale in every thread.
+__device__ float cta_rms_scale(Ctx& c, uint32_t xraw, int size) {
     const int ept = (size - 1) / 1024 + 1;
-    for (int vw = c.warp; vw < 32; vw += c.nwc) {
-        const int vt = vw * 32 + c.lane;
-        float ss = 0.0f;
+    for (int vw0 = c.warp; vw0 < 32; vw0 += 4 * c.nwc) {      // up to four virtual warps per pass, chains interleaved
+        float ss[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         for (int i = 0; i < ept; i++) {
-            const int idx = vt + i * 1024;
-            if (idx < size) {
-                const float v = h2f_bits(ld_cg_u16(x + idx));
-                ss = __fmaf_rn(v, v, ss);
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int idx = (vw0 + r * c.nwc) * 32 + c.lane + i * 1024;
+                if (vw0 + r * c.nwc < 32 && idx < size) {
+                    const float v = h2f_bits(lds_u16(xraw + idx * 2));
+                    ss[r] = __fmaf_rn(v, v, ss[r]);
+                }
             }
         }
-        ss = warp_tree_sum(ss);
-        if (c.lane == 0) c.red[vw] = ss;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const float tot = warp_tree_sum(ss[r]);
+            if (c.lane == 0 && vw0 + r * c.nwc < 32) c.red[vw0 + r * c.nwc] = tot;
+        }
     }
     named_bar(kBarAll, c.nthreads);
     float tot = c.red[0];
@@ -373,50 +450,40 @@ __device__ __forceinline__ uint32_t norm_h(uint32_t xh, uint32_t wh, float scale
 }
 __device__ __forceinline__ uint32_t word_of(const uint4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
 
-// cooperative copy of `nwords` 32-bit words global -> shared (loads batched four deep per thread)
-__device__ __forceinline__ void copy_words(const Ctx& c, uint32_t dst, const uint32_t* src, int nwords) {
-    for (int base = c.ctid; base < nwords; base += 4 * c.nthreads) {
-        uint32_t v[4];
+// RMSNorm weights of the coming op, fetched while the grid barrier is pending (they do not depend on it)
+constexpr int kNormVecs = 3;
+struct NormRegs {
+    uint4 w[kNormVecs];
+};
+__device__ __forceinline__ void load_norm_regs(const Ctx& c, const Op& op, NormRegs& nr) {
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const int e = base + r * c.nthreads;
-            v[r] = (e < nwords) ? ldg_stream_u32(src + e) : 0u;
-        }
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const int e = base + r * c.nthreads;
-            if (e < nwords) asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst + e * 4), "r"(v[r]) : "memory");
-        }
+    for (int r = 0; r < kNormVecs; r++) {
+        const int u = c.ctid + r * c.nthreads;
+        nr.w[r] = make_uint4(0, 0, 0, 0);
+        if (op.norm_w != nullptr && u * 8 < op.K) nr.w[r] = ldg_stream_v4(op.norm_w + u * 8);
     }
 }
 
-// Scales and zero points of the columns this CTA owns in the current op -> shared memory.
-//   GEMV: [scales: ncol x G halfs][zeros: ncol x zh words], columns in concatenated (q|k|v) order
-//   FFN : [gate scales][up scales][gate zeros][up zeros], nout outputs each
-// Returns the byte offset of the zero-point block (GEMV) / of one block to the next (FFN uses the same helper).
-__device__ void stage_meta(Ctx& c, const Op& op, int t0, int t1) {
-    const int G = q4_groups(op.K), zh = q4_zh(op.K);
-    if (op.kind == OP_FFN) {
-        const int o0 = t0 * 2, nout = (t1 - t0) * 2;
-        const int sw = nout * G / 2, zw = nout * zh;          // words per block (nout even: G*nout/2 is whole)
-        for (int m = 0; m < 2; m++) {
-            copy_words(c, c.sm.meta + (m * sw) * 4, reinterpret_cast<const uint32_t*>(op.seg[m].s + (size_t)o0 * G), sw);
-            copy_words(c, c.sm.meta + (2 * sw + m * zw) * 4, op.seg[m].z + (size_t)o0 * zh, zw);
-        }
-    } else {
-        const int c0 = t0 * 4, ncol = (t1 - t0) * 4;
-        const int zoff = ncol * G * 2;
-        int done = 0;
-        while (done < ncol) {                                 // one piece per matrix the range touches
-            int seg, col;
-            gemv_locate(op, c0 + done, seg, col);
-            int n = op.seg[seg].ncols - col;
-            if (n > ncol - done) n = ncol - done;
-            copy_words(c, c.sm.meta + done * G * 2, reinterpret_cast<const uint32_t*>(op.seg[seg].s + (size_t)col * G), n * G / 2);
-            copy_words(c, c.sm.meta + zoff + done * zh * 4, op.seg[seg].z + (size_t)col * zh, n * zh);
-            done += n;
-        }
+// Raw copies for a normalised op: x (one coherent 16-byte load per 8 elements: the only trip to L2 the
+// activations make) and the norm weights go to shared memory as fp16 at `xraw` / `xraw + K*2`; returns the
+// RMSNorm scale.  Ends with a named barrier.
+__device__ float stage_raw_and_scale(Ctx& c, const Op& op, const half* xin, uint32_t xraw, const NormRegs& nr) {
+    const int K = op.K;
+    const uint32_t wraw = xraw + K * 2;
+    int r = 0;
+    for (int u = c.ctid; u * 8 < K; u += c.nthreads, r++) {
+        const uint4 xv = ld_cg_v4(xin + u * 8);
+        uint4 wv;
+        if (r == 0) wv = nr.w[0]; else if (r == 1) wv = nr.w[1]; else if (r == 2) wv = nr.w[2]; else wv = ldg_stream_v4(op.norm_w + u * 8);
+        sts_v4_u32(xraw + u * 16, xv);
+        sts_v4_u32(wraw + u * 16, wv);
+        if (op.emb != nullptr && blockIdx.x == 0 && op.x_copy != nullptr) *reinterpret_cast<uint4*>(op.x_copy + u * 8) = xv;
     }
+    named_bar(kBarAll, c.nthreads);
+    trace_mark(c, 6);                             // raw x and norm weights are in shared memory
+    const float scale = cta_rms_scale(c, xraw, K);
+    trace_mark(c, 7);                             // RMSNorm scale known
+    return scale;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -425,36 +492,57 @@ __device__ void stage_meta(Ctx& c, const Op& op, int t0, int t1) {
 // (the swap keeps its two 16-byte weight loads bank-conflict free).  Pair (trip t, j, i) = (x[t*1024 + A*32 + i],
 // x[t*1024 + B*32 + i]) lives at byte  t*4096 + (i>>1)*256 + j*16 + (i&1)*8, so that one 16-byte load per thread
 // fetches two pairs and the 16 threads of a half-warp read 256 contiguous bytes.
+// The caller has already passed a named barrier: nobody reads the staging area any more.
 // ------------------------------------------------------------------------------------------------
-__device__ void stage_x_pairs(Ctx& c, const Op& op, int t0, int t1) {
+__device__ void stage_x_pairs(Ctx& c, const Op& op, const NormRegs& nr) {
     const int K = op.K;
     const half* xin = op.x;
-    named_bar(kBarAll, c.nthreads);   // every warp is done reading the previous op's staging areas
-    stage_meta(c, op, t0, t1);
     if (op.emb != nullptr) {
         const int token = op.tokens[c.pos];
         xin = op.emb + (size_t)token * K;
-        if (blockIdx.x == 0 && op.x_copy != nullptr)
-            for (int k = c.ctid; k < K; k += c.nthreads) op.x_copy[k] = xin[k];
     }
     const bool norm = (op.norm_w != nullptr);
+    const uint32_t xraw = c.sm.xs + op.T * 4096;      // raw fp16 x and norm weights sit behind the pairs
     float scale = 1.0f;
-    if (norm) scale = cta_rms_scale(c, xin, K);
+    if (norm) {
+        scale = stage_raw_and_scale(c, op, xin, xraw, nr);
+    } else if (op.emb != nullptr && blockIdx.x == 0 && op.x_copy != nullptr) {
+        for (int k = c.ctid; k < K; k += c.nthreads) op.x_copy[k] = xin[k];
+    }
     const int units = op.T * 64;      // (t, i8, j): 8 pairs each
-    for (int u = c.ctid; u < units; u += c.nthreads) {
-        const int t = u >> 6, i8 = (u >> 4) & 3, j = u & 15, sw = (j >> 2) & 1;
-        const int k0 = t * 1024 + (2 * j + sw) * 32 + i8 * 8, k1 = t * 1024 + (2 * j + 1 - sw) * 32 + i8 * 8;
-        if (k0 >= K) continue;        // K % 64 == 0: both lanes of a thread are live or dead together
-        const uint4 r0 = ld_cg_v4(xin + k0), r1 = ld_cg_v4(xin + k1);
-        uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
-        if (norm) { n0 = ldg_stream_v4(op.norm_w + k0); n1 = ldg_stream_v4(op.norm_w + k1); }
-        const uint32_t dst = c.sm.xs + t * 4096 + (i8 * 4) * 256 + j * 16;
+    constexpr int UB = 3;             // units in flight per thread (all loads first: one round trip to L2, not three)
+    for (int ub = c.ctid; ub < units; ub += UB * c.nthreads) {
+        uint4 r0[UB], r1[UB], n0[UB], n1[UB];
 #pragma unroll
-        for (int q = 0; q < 4; q++) {      // word q holds elements 2q, 2q+1
-            const uint32_t a = word_of(r0, q), b = word_of(r1, q), na = word_of(n0, q), nb = word_of(n1, q);
-            const float a0 = h2f_bits(norm_h(a & 0xFFFFu, na & 0xFFFFu, scale, norm)), a1 = h2f_bits(norm_h(a >> 16, na >> 16, scale, norm));
-            const float b0 = h2f_bits(norm_h(b & 0xFFFFu, nb & 0xFFFFu, scale, norm)), b1 = h2f_bits(norm_h(b >> 16, nb >> 16, scale, norm));
-            sts_v4(dst + q * 256, a0, b0, a1, b1);
+        for (int v = 0; v < UB; v++) {
+            const int u = ub + v * c.nthreads;
+            const int t = u >> 6, i8 = (u >> 4) & 3, j = u & 15, sw = (j >> 2) & 1;
+            const int k0 = t * 1024 + (2 * j + sw) * 32 + i8 * 8, k1 = t * 1024 + (2 * j + 1 - sw) * 32 + i8 * 8;
+            r0[v] = r1[v] = n0[v] = n1[v] = make_uint4(0, 0, 0, 0);
+            if (u < units && k0 < K) {        // K % 64 == 0: both lanes of a thread are live or dead together
+                if (norm) {
+                    r0[v] = lds_v4(xraw + k0 * 2); r1[v] = lds_v4(xraw + k1 * 2);
+                    n0[v] = lds_v4(xraw + K * 2 + k0 * 2); n1[v] = lds_v4(xraw + K * 2 + k1 * 2);
+                } else {
+                    r0[v] = ld_cg_v4(xin + k0); r1[v] = ld_cg_v4(xin + k1);
+                }
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < UB; v++) {
+            const int u = ub + v * c.nthreads;
+            const int t = u >> 6, i8 = (u >> 4) & 3, j = u & 15, sw = (j >> 2) & 1;
+            const int k0 = t * 1024 + (2 * j + sw) * 32 + i8 * 8;
+            if (u < units && k0 < K) {
+                const uint32_t dst = c.sm.xs + t * 4096 + (i8 * 4) * 256 + j * 16;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {      // word q holds elements 2q, 2q+1
+                    const uint32_t a = word_of(r0[v], q), b = word_of(r1[v], q), na = word_of(n0[v], q), nb = word_of(n1[v], q);
+                    const float a0 = h2f_bits(norm_h(a & 0xFFFFu, na & 0xFFFFu, scale, norm)), a1 = h2f_bits(norm_h(a >> 16, na >> 16, scale, norm));
+                    const float b0 = h2f_bits(norm_h(b & 0xFFFFu, nb & 0xFFFFu, scale, norm)), b1 = h2f_bits(norm_h(b >> 16, nb >> 16, scale, norm));
+                    sts_v4(dst + q * 256, a0, b0, a1, b1);
+                }
+            }
         }
     }
     named_bar(kBarAll, c.nthreads);
@@ -548,10 +636,15 @@ __device__ __forceinline__ void ring_release(const Ctx& c, const RingPos& r) {
     mbar_arrive(c.sm.empty(r.slot));
 }
 
-__device__ void run_q4(Ctx& c, const Op& op) {
+__device__ void run_q4(Ctx& c, const Op& op, const NormRegs& nr) {
     int t0, t1;
     cta_task_range(op, blockIdx.x, gridDim.x, t0, t1);
-    stage_x_pairs(c, op, t0, t1);
+    stage_x_pairs(c, op, nr);
+    const int mb = c.mcount & 1;
+    const uint32_t meta = c.sm.mbuf(mb);
+    trace_mark(c, 2);                                    // activations staged
+
+    mbar_wait(c.sm.mfull(mb), (c.mcount >> 1) & 1);      // scales / zero points of this op have landed
     const int K = op.K, T = op.T, G = q4_groups(K), zh = q4_zh(K), colb = q4_col_bytes(K);
     const int cps = op.cps, spt = op.spt;
     const bool dual = (op.kind == OP_FFN);
@@ -569,8 +662,8 @@ __device__ void run_q4(Ctx& c, const Op& op) {
         if (dual) {
             const int nout = (t1 - t0) * 2, lo = (task - t0) * 2 + h;      // local output index
             col = task * 2 + h;
-            scol0 = c.sm.meta + lo * G * 2;                         scol1 = scol0 + nout * G * 2;
-            zcol0 = c.sm.meta + 2 * nout * G * 2 + lo * zh * 4;     zcol1 = zcol0 + nout * zh * 4;
+            scol0 = meta + lo * G * 2;                         scol1 = scol0 + nout * G * 2;
+            zcol0 = meta + 2 * nout * G * 2 + lo * zh * 4;     zcol1 = zcol0 + nout * zh * 4;
             // slot: [gate cps columns][up cps columns]; output h of the task is column h % cps of slot h / cps
             RingPos r = rp;
             if (h >= cps) ring_next(c, r);                            // cps == 1: second output sits in the second slot
@@ -580,8 +673,8 @@ __device__ void run_q4(Ctx& c, const Op& op) {
             const int ncol = (t1 - t0) * 4, lc = (task - t0) * 4 + 2 * h;  // local index of my first column
             gemv_locate(op, task * 4, seg, col);
             col += 2 * h;
-            scol0 = c.sm.meta + lc * G * 2;                         scol1 = scol0 + G * 2;
-            zcol0 = c.sm.meta + ncol * G * 2 + lc * zh * 4;         zcol1 = zcol0 + zh * 4;
+            scol0 = meta + lc * G * 2;                         scol1 = scol0 + G * 2;
+            zcol0 = meta + ncol * G * 2 + lc * zh * 4;         zcol1 = zcol0 + zh * 4;
             // column i (0..3) of the task is column i % cps of slot i / cps
             RingPos r = rp;
             const int i0 = 2 * h, i1 = 2 * h + 1;
@@ -590,6 +683,7 @@ __device__ void run_q4(Ctx& c, const Op& op) {
             if (i1 / cps != i0 / cps) ring_next(c, r);
             w1 = c.sm.slot(r.slot) + (i1 % cps) * colb;
         }
+        if (task == t0) trace_mark(c, 3);                 // warp 0: first task's weights are in shared memory
         w0 += j * 32 + sw * 16;
         w1 += j * 32 + sw * 16;
         unsigned long long acc0 = 0ull, acc1 = 0ull;
@@ -627,25 +721,29 @@ __device__ void run_q4(Ctx& c, const Op& op) {
             }
         }
     }
+    trace_mark(c, 4);                                    // warp 0 has finished its tasks
     c.qbase += (unsigned)(t1 - t0) * spt;
+    c.meta_pending = mb;
+    c.mcount++;
 }
 
 // ------------------------------------------------------------------------------------------------
 // fp16 classifier consumer (mat_vec_kernel, gpu_kernels.h:109-139).  Reference lane L chains
 // k = (trip*32 + L)*8 + el over trips of 256 k; one thread is one reference lane of four rows.
 // ------------------------------------------------------------------------------------------------
-__device__ void run_cls(Ctx& c, const Op& op) {
+__device__ void run_cls(Ctx& c, const Op& op, const NormRegs& nr) {
     const int n = op.K, T = op.T, lane = c.lane, cps = op.cps, spt = op.spt;
-    // ---- stage x as fp16 (through the fused RMSNorm) ----
-    named_bar(kBarAll, c.nthreads);
+    // ---- stage x as fp16 (through the fused RMSNorm); the caller has passed a named barrier ----
     {
         const bool norm = (op.norm_w != nullptr);
+        const uint32_t xraw = c.sm.xs + ((n * 2 + 127) & ~127);
         float scale = 1.0f;
-        if (norm) scale = cta_rms_scale(c, op.x, n);
+        if (norm) scale = stage_raw_and_scale(c, op, op.x, xraw, nr);
         for (int u = c.ctid; u * 8 < n; u += c.nthreads) {
-            uint4 xv = ld_cg_v4(op.x + u * 8);
+            uint4 xv;
             if (norm) {
-                const uint4 wv = ldg_stream_v4(op.norm_w + u * 8);
+                xv = lds_v4(xraw + u * 16);
+                const uint4 wv = lds_v4(xraw + n * 2 + u * 16);
                 uint32_t* xw = &xv.x;
                 const uint32_t* ww = &wv.x;
 #pragma unroll
@@ -654,6 +752,8 @@ __device__ void run_cls(Ctx& c, const Op& op) {
                     const uint32_t hi = norm_h(xw[q] >> 16, ww[q] >> 16, scale, true);
                     xw[q] = lo | (hi << 16);
                 }
+            } else {
+                xv = ld_cg_v4(op.x + u * 8);
             }
             sts_v4_u32(c.sm.xs + u * 16, xv);
         }
@@ -715,7 +815,8 @@ __device__ void run_cls(Ctx& c, const Op& op) {
 // (RoPERotation_kernel :332-355, mat_vec_kernel_simple :142-168, softmax_kernel :357-401,
 //  vec_mat_kernel :279-329).  The reference's 1024-thread reductions are replayed with virtual threads.
 // ------------------------------------------------------------------------------------------------
-__device__ void run_attn(Ctx& c, const Op& op) {
+template <int NSER>
+__device__ void run_attn_t(Ctx& c, const Op& op) {
     const int hs = op.head_size, nt = c.nthreads, tid = c.ctid, lane = c.lane, warp = c.warp;
     float* qs = reinterpret_cast<float*>(c.scratch);      // hs
     float* krow = qs + hs;                                 // hs: rotated k row of this step
@@ -754,22 +855,52 @@ __device__ void run_attn(Ctx& c, const Op& op) {
             }
         }
         named_bar(kBarAll, nt);
-        // ---- scores: one warp per t ----
+        trace_mark(c, 2);
+        // ---- scores: one warp per t (lane chain over j = 32 i + lane, gpu_kernels.h:154-159) ----
+        // Rows are taken eight at a time with every load issued before the first use: one trip to L2 per batch.
         const int nser = hs / 32;
-        for (int t = warp; t < size; t += c.nwc) {
-            float sum = 0.0f;
-            if (t == pos) {
-                for (int i = 0; i < nser; i++) sum = __fmaf_rn(krow[i * 32 + lane], qs[i * 32 + lane], sum);
-            } else {
-                const half* kr = kbase + (size_t)t * op.kv_stride;
-                for (int i = 0; i < nser; i++)
-                    sum = __fmaf_rn(h2f_bits(ld_cg_u16(kr + i * 32 + lane)), qs[i * 32 + lane], sum);
+        if (NSER > 0) {
+            constexpr int TB = 8, NS = NSER > 0 ? NSER : 1;
+            for (int tb = warp; tb < size; tb += TB * c.nwc) {
+                uint32_t kv[TB][NS];
+#pragma unroll
+                for (int u = 0; u < TB; u++) {
+                    const int t = tb + u * c.nwc;
+                    const half* kr = kbase + (size_t)t * op.kv_stride;
+#pragma unroll
+                    for (int i = 0; i < NS; i++) kv[u][i] = (t < pos) ? ld_cg_u16(kr + i * 32 + lane) : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < TB; u++) {
+                    const int t = tb + u * c.nwc;
+                    float sum = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < NS; i++) {
+                        const float kval = (t == pos) ? krow[i * 32 + lane] : h2f_bits(kv[u][i]);
+                        sum = __fmaf_rn(kval, qs[i * 32 + lane], sum);
+                    }
+                    sum = warp_tree_sum(sum);
+                    sum = __fmul_rn(sum, op.att_alpha);
+                    if (lane == 0 && t < size) att[t] = __half2float(__float2half_rn(sum));
+                }
             }
-            sum = warp_tree_sum(sum);
-            sum = __fmul_rn(sum, op.att_alpha);
-            if (lane == 0) att[t] = __half2float(__float2half_rn(sum));
+        } else {
+            for (int t = warp; t < size; t += c.nwc) {
+                float sum = 0.0f;
+                if (t == pos) {
+                    for (int i = 0; i < nser; i++) sum = __fmaf_rn(krow[i * 32 + lane], qs[i * 32 + lane], sum);
+                } else {
+                    const half* kr = kbase + (size_t)t * op.kv_stride;
+                    for (int i = 0; i < nser; i++)
+                        sum = __fmaf_rn(h2f_bits(ld_cg_u16(kr + i * 32 + lane)), qs[i * 32 + lane], sum);
+                }
+                sum = warp_tree_sum(sum);
+                sum = __fmul_rn(sum, op.att_alpha);
+                if (lane == 0) att[t] = __half2float(__float2half_rn(sum));
+            }
         }
         named_bar(kBarAll, nt);
+        trace_mark(c, 3);
         // ---- softmax (idle reference threads seed the max with 0, gpu_kernels.h:374) ----
         float mx = (size < 1024) ? 0.0f : -INFINITY;
         for (int i = tid; i < size; i += nt) mx = fmaxf(mx, att[i]);
@@ -799,8 +930,47 @@ __device__ void run_attn(Ctx& c, const Op& op) {
             if (op.att_out != nullptr) op.att_out[(size_t)h * size + i] = pr;
         }
         named_bar(kBarAll, nt);
+        trace_mark(c, 4);
         // ---- PV: reference lane tx chains t = 32 e + tx (e ascending); then the cub tree over tx ----
-        {
+        // A lane owns hs/32 consecutive outputs; the V rows of eight steps of a chain are loaded before the first FMA.
+        if (NSER > 0) {
+            constexpr int EB = 8, NS = NSER > 0 ? NSER : 1;
+            for (int tx = warp; tx < 32; tx += c.nwc) {
+                float a[NS];
+#pragma unroll
+                for (int q = 0; q < NS; q++) a[q] = 0.0f;
+                for (int t0 = tx; t0 < size; t0 += 32 * EB) {
+                    uint32_t vv[EB][(NS + 1) / 2];
+#pragma unroll
+                    for (int e = 0; e < EB; e++) {
+                        const int t = t0 + 32 * e;
+                        const half* vr = vbase + (size_t)t * op.kv_stride + lane * NS;
+#pragma unroll
+                        for (int q2 = 0; q2 < (NS + 1) / 2; q2++) vv[e][q2] = 0u;
+                        if (t < size) {
+                            if (NS == 4) { const uint2 r = ld_cg_v2(vr); vv[e][0] = r.x; vv[e][1] = r.y; }
+                            else if (NS == 8) { const uint4 r = ld_cg_v4(vr); vv[e][0] = r.x; vv[e][1] = r.y; vv[e][2] = r.z; vv[e][3] = r.w; }
+                            else if (NS == 2) { asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(vv[e][0]) : "l"(vr)); }
+                            else vv[e][0] = ld_cg_u16(vr);
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < EB; e++) {
+                        const int t = t0 + 32 * e;
+                        if (t < size) {
+                            const float pt = att[t];
+#pragma unroll
+                            for (int q = 0; q < NS; q++) {
+                                const uint32_t word = vv[e][q >> 1];
+                                a[q] = __fmaf_rn(h2f_bits((q & 1) ? (word >> 16) : (word & 0xFFFFu)), pt, a[q]);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < NS; q++) part[tx * hs + lane * NS + q] = a[q];
+            }
+        } else {
             const int per_lane = hs / 32;
             for (int tx = warp; tx < 32; tx += c.nwc) {
                 float a[8];
@@ -819,6 +989,7 @@ __device__ void run_attn(Ctx& c, const Op& op) {
             }
         }
         named_bar(kBarAll, nt);
+        trace_mark(c, 6);
         for (int i = tid; i < hs; i += nt) {
             float v[32];
 #pragma unroll
@@ -830,7 +1001,14 @@ __device__ void run_attn(Ctx& c, const Op& op) {
             op.attn_out[(size_t)h * hs + i] = __float2half_rn(v[0]);
         }
         named_bar(kBarAll, nt);
+        trace_mark(c, 7);
     }
+}
+
+__device__ void run_attn(Ctx& c, const Op& op) {
+    if (op.head_size == 128) run_attn_t<4>(c, op);
+    else if (op.head_size == 64) run_attn_t<2>(c, op);
+    else run_attn_t<0>(c, op);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -842,7 +1020,27 @@ __device__ void run_argmax(Ctx& c, const Op& op, int write_token) {
     int* sidx = reinterpret_cast<int*>(c.red + 32);
     float max_val = -INFINITY;
     int max_pos = 0x7fffffff;
-    for (int i = c.ctid; i < op.vocab; i += c.nthreads) {
+    // 8 logits per 16-byte load, four loads in flight per thread; ascending index order per thread keeps "first maximum"
+    const int nvec = op.vocab >> 3;
+    for (int vb = c.ctid; vb < nvec; vb += 4 * c.nthreads) {
+        uint4 lv[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int vi = vb + r * c.nthreads;
+            lv[r] = (vi < nvec) ? ld_cg_v4(op.logits + (size_t)vi * 8) : make_uint4(0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int vi = vb + r * c.nthreads;
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const uint32_t word = word_of(lv[r], e >> 1);
+                const float v = h2f_bits((e & 1) ? (word >> 16) : (word & 0xFFFFu));
+                if (vi < nvec && v > max_val) { max_val = v; max_pos = vi * 8 + e; }
+            }
+        }
+    }
+    for (int i = (nvec << 3) + c.ctid; i < op.vocab; i += c.nthreads) {
         const float v = h2f_bits(ld_cg_u16(op.logits + i));
         if (v > max_val) { max_val = v; max_pos = i; }
     }
@@ -857,8 +1055,7 @@ __device__ void run_argmax(Ctx& c, const Op& op, int write_token) {
     if (c.ctid == 0) {
         for (int w = 1; w < c.nwc; w++)
             if (smax[w] > max_val || (smax[w] == max_val && sidx[w] < max_pos)) { max_val = smax[w]; max_pos = sidx[w]; }
-        int token_pos = *op.pos_host;
-        token_pos++;
+        int token_pos = c.pos + 1;     // SharedData::pos and RunState::pos move together (gpu_kernels.h:486-491); no PCIe read
         if (write_token) op.tokens_out[token_pos] = max_pos;
         __threadfence_system();
         *op.pos_host = token_pos;      // unblocks the CPU (pinned host memory)
@@ -880,7 +1077,8 @@ __global__ void __launch_bounds__(512, 1) interp_kernel(const __grid_constant__ 
     sm.laps = sm.bars + kLapOffset;
     sm.xs = sm.bars + kCtrlBytes;
     sm.meta = sm.xs + P.xs_bytes;
-    sm.ring = sm.meta + P.meta_bytes;
+    sm.meta_bytes = P.meta_bytes;
+    sm.ring = sm.meta + 2 * P.meta_bytes;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.nslots; s++) {
@@ -888,6 +1086,7 @@ __global__ void __launch_bounds__(512, 1) interp_kernel(const __grid_constant__ 
             mbar_init(sm.empty(s), 1);
             reinterpret_cast<volatile unsigned*>(smem + kLapOffset)[s] = 0u;
         }
+        for (int b = 0; b < 2; b++) { mbar_init(sm.mfull(b), 1); mbar_init(sm.mempty(b), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -904,23 +1103,42 @@ __global__ void __launch_bounds__(512, 1) interp_kernel(const __grid_constant__ 
     c.scratch = smem + kCtrlBytes;
     c.nwc = P.nwc; c.nthreads = P.nwc * 32; c.warp = warp; c.lane = lane; c.ctid = threadIdx.x;
     c.pos = (P.pPos != nullptr) ? *P.pPos : 0;
-    c.qbase = 0; c.nsync = 0;
+    c.qbase = 0; c.mcount = 0; c.meta_pending = -1; c.nsync = 0; c.tr = nullptr;
 
+    const Op& op = *reinterpret_cast<const Op*>(smem + kOpOffset);
     for (int o = 0; o < P.nops; o++) {
-        const Op& op = ops[o];
-        if (op.sync_before) {
-            c.nsync++;
-            grid_barrier(P.sync, c.nsync * gridDim.x, c.nthreads, c.ctid);
+        // every warp has left the previous op: its staging areas, scale/zero buffer and op copy are free
+        named_bar(kBarAll, c.nthreads);
+        if (c.ctid < (int)(sizeof(Op) / 4))        // the op goes to shared memory: its fields are read many times per task
+            reinterpret_cast<uint32_t*>(smem + kOpOffset)[c.ctid] = reinterpret_cast<const uint32_t*>(ops + o)[c.ctid];
+        const int sync_before = ops[o].sync_before;
+        trace_mark(c, 5);                          // previous op: every warp of this CTA is done
+        c.tr = (P.trace != nullptr && o == P.trace_op) ? P.trace + 2048 + blockIdx.x * 8 : nullptr;
+        trace_mark(c, 0);                          // this CTA arrives at the op
+        if (c.ctid == 0) {
+            if (c.meta_pending >= 0) mbar_arrive(sm.mempty(c.meta_pending));
+            if (sync_before) grid_arrive(P.sync);
         }
+        c.meta_pending = -1;
+        NormRegs nr;
+        load_norm_regs(c, ops[o], nr);             // in flight while the grid barrier completes
+        if (sync_before) {
+            c.nsync++;
+            if (c.ctid == 0) grid_wait(P.sync, c.nsync * gridDim.x);
+        }
+        named_bar(kBarAll, c.nthreads);
+        if (P.trace != nullptr && blockIdx.x == 0 && c.ctid == 0) P.trace[o] = global_ns();
+        trace_mark(c, 1);                          // grid barrier passed
         switch (op.kind) {
             case OP_GEMV:
-            case OP_FFN: run_q4(c, op); break;
-            case OP_CLS: run_cls(c, op); break;
+            case OP_FFN: run_q4(c, op, nr); break;
+            case OP_CLS: run_cls(c, op, nr); break;
             case OP_ATTN: run_attn(c, op); break;
             case OP_ARGMAX: run_argmax(c, op, (P.write_token >= 0) ? P.write_token : op.write_token); break;
             default: break;
         }
     }
+    if (P.trace != nullptr && blockIdx.x == 0 && c.ctid == 0) P.trace[P.nops] = global_ns();
     // leave the barrier counters at zero for the next launch: the last CTA out resets them
     if (c.nsync > 0) {
         named_bar(kBarAll, c.nthreads);

@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""Development aid (run under gpurun): per-op time line of one fused decode step at a given position."""
+import ctypes as C
+import collections
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import llama_cu_awq_b200 as E
+import bench as B
+
+model = sys.argv[1] if len(sys.argv) > 1 else "7b"
+npos = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+lib = E.lib()
+assert lib.lq4_init(0) == 0
+cfg = B.model_cfg(model)
+path, tok = B.ensure_files(lib, E, model, cfg)
+t = E.Transformer()
+lib.lq4_build_transformer(C.byref(t), path.encode(), 0)
+s = E.Sampler()
+lib.lq4_build_sampler(C.byref(s), cfg["vocab_size"], 0.0, 0.9, 1)
+bos = (C.c_int * 1)(1)
+lib.lq4_reset(C.byref(t), bos, 1)
+lib.lq4_set_option(b"trace", 1)
+trace_op = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+lib.lq4_set_option(b"trace_op", trace_op)
+for i in range(npos):
+    lib.lq4_enqueue_step(C.byref(t), C.byref(s), i + 1, 1)
+assert lib.lq4_stream_synchronize() == 0
+N = 4096
+ts = (C.c_ulonglong * N)()
+kinds = (C.c_int * N)()
+n = lib.lq4_debug_trace(ts, kinds, N)
+names = {0: "gemv", 1: "ffn", 2: "cls", 3: "attn", 4: "argmax"}
+agg = collections.OrderedDict()
+for i in range(n - 1):
+    k = (names[kinds[i] // 100000], kinds[i] % 100000)
+    a = agg.setdefault(k, [0, 0.0])
+    a[0] += 1
+    a[1] += (ts[i + 1] - ts[i]) / 1000.0
+total = (ts[n - 1] - ts[0]) / 1000.0
+print(f"step at pos {npos - 1}: {total:.1f} us over {n - 1} ops")
+for k, (cnt, us) in agg.items():
+    print(f"  {k[0]:7s} K={k[1]:6d}: {cnt:4d} ops, {us:9.1f} us total, {us / cnt:7.2f} us each ({100 * us / total:5.1f}%)")
+first = [(names[kinds[i] // 100000], kinds[i] % 100000, (ts[i + 1] - ts[i]) / 1000.0) for i in range(5, 12)]
+print("  layer 1 ops:", first)
+
+# phases of op `trace_op` on every CTA: 0 arrive, 1 barrier passed, 2 staged, 3 first weights, 4 warp0 done, 5 all warps done
+import numpy as np
+nb = min(148, cfg["n_heads"]) if names[kinds[trace_op] // 100000] == "attn" else 148
+ph = np.array([[ts[2048 + b * 8 + k] for k in range(8)] for b in range(nb)], dtype=np.float64)
+t0 = ph[:, 1].min()
+rel = (ph - t0) / 1000.0
+print(f"op {trace_op} ({names[kinds[trace_op] // 100000]} K={kinds[trace_op] % 100000}) phases in us relative to the first CTA past the barrier [min / median / max over CTAs]:")
+for k, name in enumerate(["arrive(prev done)", "barrier passed", "x staged", "first weights", "warp0 done", "all warps done", "raw x in smem", "rms scale known"]):
+    print(f"  {name:18s} {rel[:, k].min():8.2f} {np.median(rel[:, k]):8.2f} {rel[:, k].max():8.2f}")
