@@ -13,9 +13,9 @@ K=256 is the reference's `-n 256`.
   e2e    : tokens/s through the C-ABI host-buffer call lq4_generate_tokens (prompt tokens in host
            memory, ids out to host memory; the per-token pinned-memory token/position hand-off and the
            host wait are inside its timed loop, as in the reference's generate()).
-  roofline: dominant kernel = the fused gate/up+SiLU INT4 GEMV (45% of per-layer bytes), timed alone
-           with CUDA events over all layers' weights in rotation (1.5 GB >> L2), algorithmic bytes /
-           duration against MEASURED_PEAKS.json; roofline_step is the same fraction for the whole token.
+  roofline: dominant kernel = interp_kernel, the persistent kernel that IS the decode step (one launch per
+           token): algorithmic bytes (weights + KV) / mean launch duration against MEASURED_PEAKS.json;
+           roofline_ffn_op is the largest single op (gate/up+SiLU) alone through the operator API.
   cpu_baseline: the oracle port (oracle/cpu_ref.c) single-threaded on a bounded sample.
 --impl reference: the reference has no CPU implementation (CUDA only), so this arm times the oracle
   port with all host threads on a bounded sample, and also reports the UNMODIFIED reference CUDA build
@@ -272,9 +272,26 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_val = (n - 1) / float(te.item())
 
-    # ---- roofline of the dominant kernel: fused gate/up+SiLU GEMV, all layers in rotation ----
+    # ---- roofline ----
+    # The decode step is ONE launch of the persistent kernel (interp_kernel), so the dominant kernel's launch
+    # duration is ms/K measured above with CUDA events on the engine stream.  Algorithmic bytes per launch =
+    # weights + KV cache rows touched (DESIGN.md "bytes per unit"), averaged over the K positions.
     peak, peak_src = load_peaks()
     d, h, L = cfg["dim"], cfg["hidden_dim"], cfg["n_layers"]
+    wbytes = E.weight_bytes_per_token(cfg)
+    kvbytes = sum(E.kv_bytes_at(cfg, p) for p in range(K)) / K
+    step_gbs = (wbytes + kvbytes) / (ms / K * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "step_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(args.model, {}).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": "interp_kernel (whole decode step: 1 launch per token)", "achieved": step_gbs, "peak": peak,
+                "unit": "GB/s", "frac": step_gbs / peak, "traffic": traffic, "bytes_per_launch": wbytes + kvbytes,
+                "us_per_launch": ms / K * 1000.0, "peak_source": peak_src,
+                "how": "algorithmic bytes (weights + mean KV over the K positions) / mean launch duration, CUDA events on the engine stream; "
+                       "traffic = dram read+write of one launch from the committed ncu --set full capture (profiles/)"}
+    # the largest single op (gate/up+SiLU INT4 GEMV, 45% of a layer's bytes) alone through the operator API, all layers' weights in rotation
     ffn_bytes = 2 * h * (E.packed_weight_height(d) * 4 + E.packed_zeros_height(d) * 4 + E.num_groups(d) * 2)
     layers = t.weights.layers
     reps = 3
@@ -292,27 +309,22 @@ def main():
     torch.cuda.synchronize()
     ffn_us = ev0.elapsed_time(ev1) * 1000.0 / (reps * L)
     ach = ffn_bytes / (ffn_us * 1e-6) / 1e9
-    roofline = {"bound": "hbm", "kernel": "gemv_q4_kernel<GEMV_FFN> (gate/up+SiLU, K=%d N=%d)" % (d, h), "achieved": ach, "peak": peak,
-                "unit": "GB/s", "frac": ach / peak, "traffic": None, "bytes_per_launch": ffn_bytes, "us_per_launch": ffn_us,
-                "peak_source": peak_src, "how": "CUDA events on the engine stream, launches back to back over all layers' weights (> L2)"}
-    wbytes = E.weight_bytes_per_token(cfg)
-    kvbytes = sum(E.kv_bytes_at(cfg, p) for p in range(K)) / K
-    step_gbs = (wbytes + kvbytes) / (ms / K * 1e-3) / 1e9
+    roofline_ffn = {"bound": "hbm", "kernel": "interp_kernel, single op lq4_ffn_matvec_silu (K=%d N=%d), launch overhead included" % (d, h),
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "bytes_per_launch": ffn_bytes, "us_per_launch": ffn_us}
     value = world * K / (ms * 1e-3)
 
     line = {"metric": "decode tokens/sec (seq_len=1)", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int4 weights, fp16 storage, fp32 accumulate", "data": "synthetic",
             "config": {"workload": f"Llama-2-{args.model.upper()} w4-g128 random-init .bin, greedy decode -n {K}, batch 1",
-                       "l2": "inputs larger than L2 (3.6 GB of weights per step)", "parallelism": "replicas" if world > 1 else "1 GPU",
-                       "options": {"pdl": int(os.environ.get("LQ4_PDL", "1")), "fused": int(os.environ.get("LQ4_FUSED", "1"))}},
+                       "l2": "inputs larger than L2 (3.6 GB of weights per step)", "parallelism": "replicas" if world > 1 else "1 GPU"},
             "clocks": clk,
             "e2e": {"value": (e2e_val * world) if e2e_val else None, "unit": "tokens/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 8,
-                    "how": "lq4_generate_tokens(host prompt ids -> host ids), wall clock of its loop, pipelined launch"},
-            "gpu_launches": K * (5 * cfg["n_layers"] + 2),
+                    "how": "lq4_generate_tokens(host prompt ids -> host ids), wall clock of its loop, pipelined launch; per step the kernel "
+                           "reads the token id from pinned host memory and writes the new id and position back to it"},
+            "gpu_launches": K,
             "roofline": roofline,
-            "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
-                              "bytes_per_step": wbytes + kvbytes, "peak_source": peak_src}}
+            "roofline_ffn_op": roofline_ffn}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline_sample(path, cfg, 1)
