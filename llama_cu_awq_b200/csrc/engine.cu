@@ -190,10 +190,7 @@ long time_in_ms() {   // llama2_q4.cu:400-405
 }
 
 // ------------------------------------------------------------------------------- persistent kernel: plans and ops
-int attn_scratch_bytes(int head_size, int max_seq) {
-    const int floats = 2 * head_size + ((max_seq + 3) & ~3) + 32 * head_size;
-    return (floats * 4 + 127) & ~127;
-}
+int attn_scratch_bytes(int head_size, int max_seq) { return attn_fixed_bytes(head_size, max_seq) + 2 * attn_buf_bytes(head_size); }
 
 // Shared-memory plan for `nwc` consumer warps: a staging area of `xs` bytes (activations / attention scratch),
 // `meta` bytes of scales / zero points and as many ring slots of `slot` bytes as fit.
@@ -500,7 +497,7 @@ void lq4_rope_rotation(half* q, half* k, int num_heads, int num_kv_heads, int he
 
 static void fill_attn_op(Op& op, half* output, half* q, half* key_cache, half* value_cache, half* att, int num_heads,
                          int head_size, int kv_mul, int max_seq_len) {
-    if (head_size % 32 != 0 || head_size > 256) unsupported();
+    if (head_size != 32 && head_size != 64 && head_size != 128) unsupported();
     if (max_seq_len > MAX_SEQ_LEN_SMEM_KERNEL) {
         // the reference switches to softmax_kernel_no_smem here (llama2_q4.cu:276-279), whose fp16
         // rounding of exp() differs; that variant is scope row f2 and not built yet.
@@ -518,6 +515,18 @@ static void fill_attn_op(Op& op, half* output, half* q, half* key_cache, half* v
 void lq4_multi_head_attention(half* output, half* q, half* key_cache, half* value_cache, half* att, int num_heads,
                               int head_size, int kv_mul, int max_seq_len, int* pPos) {
     ensure_init();
+    if (head_size != 32 && head_size != 64 && head_size != 128 && head_size % 32 == 0 && head_size <= 256 &&
+        max_seq_len <= MAX_SEQ_LEN_SMEM_KERNEL) {
+        // other head sizes: the stand-alone kernel (same arithmetic, one block of 1024 threads per head)
+        AttnParams ap = {};
+        ap.out = output; ap.q = q; ap.kcache = key_cache; ap.vcache = value_cache; ap.att_out = att;
+        ap.head_size = head_size; ap.kv_mul = kv_mul; ap.kv_stride = (num_heads * head_size) / kv_mul;
+        ap.pPos = pPos; ap.alpha = (float)(1.0 / sqrt((double)head_size)); ap.max_seq = max_seq_len;
+        const size_t smem = sizeof(float) * (size_t)(head_size + 32 + 4 + ((max_seq_len + 3) & ~3) + 32 * head_size);
+        allow_smem(attention_kernel, smem);
+        launch(attention_kernel, dim3(num_heads), dim3(kAttnThreads), smem, false, ap);
+        return;
+    }
     Op op;
     memset(&op, 0, sizeof op);
     fill_attn_op(op, output, q, key_cache, value_cache, att, num_heads, head_size, kv_mul, max_seq_len);
@@ -575,7 +584,7 @@ static NetPlan& get_net_plan(Config* p, RunState* s, TransformerWeights* w) {
     const int head_size = dim / p->n_heads;
     const int kv_dim = (p->dim * p->n_kv_heads) / p->n_heads;
     const int kv_mul = p->n_heads / p->n_kv_heads;
-    if (head_size % 32 != 0 || head_size > 256 || (head_size & 1) || p->seq_len > MAX_SEQ_LEN_SMEM_KERNEL) return np;
+    if ((head_size != 32 && head_size != 64 && head_size != 128) || p->seq_len > MAX_SEQ_LEN_SMEM_KERNEL) return np;
     LQ4_CHECK(cudaMalloc((void**)&np.kraw, sizeof(half) * kv_dim));
     const float2* rope_tab = rope_table(p->rope_theta, head_size, p->seq_len);
 

@@ -113,7 +113,7 @@ struct InterpParams {
     Op one;                // inline single op (operator API)
 };
 
-constexpr int kMaxConsumerWarps = 15;
+constexpr int kMaxConsumerWarps = 11;   // 12 warps = 3 per SM sub-partition: 168 registers per thread (a 4th warp on a sub-partition would cap them at 128)
 constexpr int kMaxSlots = 120;
 constexpr int kBarAll = 13;        // named barrier: all consumer warps
 constexpr int kCtrlBytes = 4096;   // mbarriers (first 2 KB) + reduction scratch (at 3 KB)
@@ -471,6 +471,7 @@ __device__ float stage_raw_and_scale(Ctx& c, const Op& op, const half* xin, uint
     const int K = op.K;
     const uint32_t wraw = xraw + K * 2;
     int r = 0;
+#pragma unroll 1
     for (int u = c.ctid; u * 8 < K; u += c.nthreads, r++) {
         const uint4 xv = ld_cg_v4(xin + u * 8);
         uint4 wv;
@@ -480,10 +481,7 @@ __device__ float stage_raw_and_scale(Ctx& c, const Op& op, const half* xin, uint
         if (op.emb != nullptr && blockIdx.x == 0 && op.x_copy != nullptr) *reinterpret_cast<uint4*>(op.x_copy + u * 8) = xv;
     }
     named_bar(kBarAll, c.nthreads);
-    trace_mark(c, 6);                             // raw x and norm weights are in shared memory
-    const float scale = cta_rms_scale(c, xraw, K);
-    trace_mark(c, 7);                             // RMSNorm scale known
-    return scale;
+    return cta_rms_scale(c, xraw, K);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -510,7 +508,8 @@ __device__ void stage_x_pairs(Ctx& c, const Op& op, const NormRegs& nr) {
         for (int k = c.ctid; k < K; k += c.nthreads) op.x_copy[k] = xin[k];
     }
     const int units = op.T * 64;      // (t, i8, j): 8 pairs each
-    constexpr int UB = 3;             // units in flight per thread (all loads first: one round trip to L2, not three)
+    constexpr int UB = 2;             // units in flight per thread (all loads first: one round trip to L2, not three)
+#pragma unroll 1
     for (int ub = c.ctid; ub < units; ub += UB * c.nthreads) {
         uint4 r0[UB], r1[UB], n0[UB], n1[UB];
 #pragma unroll
@@ -649,6 +648,7 @@ __device__ void run_q4(Ctx& c, const Op& op, const NormRegs& nr) {
     const int cps = op.cps, spt = op.spt;
     const bool dual = (op.kind == OP_FFN);
     const int h = c.lane >> 4, j = c.lane & 15, sw = (j >> 2) & 1;
+#pragma unroll 1
     for (int task = t0 + c.warp; task < t1; task += c.nwc) {
         // ---- my two columns: where their weights, scales and zeros are ----
         RingPos rp = ring_pos(c, c.qbase + (unsigned)(task - t0) * spt);
@@ -688,6 +688,7 @@ __device__ void run_q4(Ctx& c, const Op& op, const NormRegs& nr) {
         w1 += j * 32 + sw * 16;
         unsigned long long acc0 = 0ull, acc1 = 0ull;
         const int tlive = (K - j * 64 + 1023) >> 10;      // trips in which this thread's lanes hold data
+#pragma unroll 1
         for (int t = 0; t < T; t++) {
             if (t < tlive) {
                 const ColMeta m0 = col_meta(scol0, zcol0, t, j), m1 = col_meta(scol1, zcol1, t, j);
@@ -699,6 +700,8 @@ __device__ void run_q4(Ctx& c, const Op& op, const NormRegs& nr) {
             RingPos r = rp;
             for (int i = 0; i < spt; i++) { ring_release(c, r); ring_next(c, r); }
         }
+        if (task == t0) trace_mark(c, 6);                 // warp 0: first task done
+        else if (task == t0 + c.nwc) trace_mark(c, 7);    // warp 0: second task done
         // ---- epilogue ----
         const float v0 = halfwarp_total(acc0), v1 = halfwarp_total(acc1);
         if (j == 0) {
@@ -739,6 +742,7 @@ __device__ void run_cls(Ctx& c, const Op& op, const NormRegs& nr) {
         const uint32_t xraw = c.sm.xs + ((n * 2 + 127) & ~127);
         float scale = 1.0f;
         if (norm) scale = stage_raw_and_scale(c, op, op.x, xraw, nr);
+#pragma unroll 1
         for (int u = c.ctid; u * 8 < n; u += c.nthreads) {
             uint4 xv;
             if (norm) {
@@ -762,6 +766,7 @@ __device__ void run_cls(Ctx& c, const Op& op, const NormRegs& nr) {
 
     int t0, t1;
     cta_task_range(op, blockIdx.x, gridDim.x, t0, t1);
+#pragma unroll 1
     for (int task = t0 + c.warp; task < t1; task += c.nwc) {
         int rows = op.seg[0].ncols - task * 4;
         if (rows > 4) rows = 4;
@@ -814,32 +819,76 @@ __device__ void run_cls(Ctx& c, const Op& op, const NormRegs& nr) {
 // Attention for one head per CTA: [RoPE on q and on the new k row] -> QK^T -> softmax -> PV
 // (RoPERotation_kernel :332-355, mat_vec_kernel_simple :142-168, softmax_kernel :357-401,
 //  vec_mat_kernel :279-329).  The reference's 1024-thread reductions are replayed with virtual threads.
+//
+// K and V rows of earlier positions are staged through shared memory in tiles of kAttnTile rows with cooperative
+// 16-byte loads (one trip to L2 per tile instead of one per row); the first tile of both is fetched BEFORE the grid
+// barrier that precedes the op, since rows t < pos were written by earlier launches.
+// Scratch layout (floats unless noted): qs[hs] | krow[hs] | vrow[hs] | att[max_seq] | bufA (tile, fp16; later `part`) | bufB (tile, fp16)
 // ------------------------------------------------------------------------------------------------
+constexpr int kAttnTile = 64;
+__host__ __device__ __forceinline__ int attn_buf_bytes(int hs) {
+    const int tile = kAttnTile * hs * 2, part = 32 * hs * 4;
+    return ((tile > part ? tile : part) + 127) & ~127;
+}
+__host__ __device__ __forceinline__ int attn_fixed_bytes(int hs, int max_seq) { return ((3 * hs + ((max_seq + 3) & ~3)) * 4 + 127) & ~127; }
+
+// rows [row0, row0 + nrows) of one head (hs halfs each, kv_stride apart) -> shared memory, row-major
+__device__ __forceinline__ void attn_load_tile(const Ctx& c, uint32_t dst, const half* base, int kv_stride, int hs, int row0, int nrows) {
+    const int vsh = (hs == 128) ? 4 : (hs == 64) ? 3 : 2;  // log2(16-byte vectors per row)
+    const int total = nrows << vsh;
+    const half* src = base + (size_t)row0 * kv_stride;
+#pragma unroll 1
+    for (int b0 = c.ctid; b0 < total; b0 += 2 * c.nthreads) {
+        const int i0 = b0, i1 = b0 + c.nthreads;
+        const bool p1 = i1 < total;
+        const int r0 = i0 >> vsh, c0 = i0 & ((1 << vsh) - 1), r1 = p1 ? (i1 >> vsh) : r0, c1 = p1 ? (i1 & ((1 << vsh) - 1)) : c0;
+        const uint4 v0 = ld_cg_v4(src + (size_t)r0 * kv_stride + c0 * 8);
+        const uint4 v1 = ld_cg_v4(src + (size_t)r1 * kv_stride + c1 * 8);
+        sts_v4_u32(dst + i0 * 16, v0);
+        if (p1) sts_v4_u32(dst + i1 * 16, v1);
+    }
+}
+// before the grid barrier: first K and V tile of this CTA's (first) head
+__device__ void attn_prefetch(const Ctx& c, const Op& op) {
+    const int h = blockIdx.x, hs = op.head_size;
+    if (h >= op.n_heads || (hs & 7)) return;
+    const int kvh = h / op.kv_mul;
+    const int nrows = c.pos < kAttnTile ? c.pos : kAttnTile;
+    const uint32_t bufA = c.sm.xs + attn_fixed_bytes(hs, op.max_seq), bufB = bufA + attn_buf_bytes(hs);
+    attn_load_tile(c, bufA, op.kcache + (size_t)kvh * hs, op.kv_stride, hs, 0, nrows);
+    attn_load_tile(c, bufB, op.vcache + (size_t)kvh * hs, op.kv_stride, hs, 0, nrows);
+}
+
 template <int NSER>
-__device__ void run_attn_t(Ctx& c, const Op& op) {
+__device__ void run_attn_t(Ctx& c, const Op& op, bool prefetched) {
+    constexpr int NS = NSER;                               // hs / 32
     const int hs = op.head_size, nt = c.nthreads, tid = c.ctid, lane = c.lane, warp = c.warp;
-    float* qs = reinterpret_cast<float*>(c.scratch);      // hs
-    float* krow = qs + hs;                                 // hs: rotated k row of this step
-    float* att = krow + hs;                                // max_seq
-    float* part = att + ((op.max_seq + 3) & ~3);           // 32 * hs
+    float* qs = reinterpret_cast<float*>(c.scratch);       // hs
+    float* krow = qs + hs;                                  // hs: rotated k row of this step
+    float* vrow = krow + hs;                                // hs: v row of this step
+    float* att = vrow + hs;                                 // max_seq
+    const uint32_t bufA = c.sm.xs + attn_fixed_bytes(hs, op.max_seq), bufB = bufA + attn_buf_bytes(hs);
+    float* part = reinterpret_cast<float*>(c.scratch + attn_fixed_bytes(hs, op.max_seq));   // 32 * hs, aliases bufA
     float* red = c.red;
     const int pos = c.pos, size = pos + 1;
+#pragma unroll 1
     for (int h = blockIdx.x; h < op.n_heads; h += gridDim.x) {
         const int kvh = h / op.kv_mul;
         half* kbase = op.kcache + (size_t)kvh * hs;
         const half* vbase = op.vcache + (size_t)kvh * hs;
-        // ---- q (and the new k row): load, rotate, keep in shared memory ----
+        const bool have_tile0 = prefetched && h == (int)blockIdx.x;
+        // ---- q, the new k row (rotated here when a table is given) and the new v row -> shared memory ----
         if (op.rope_tab != nullptr) {
             for (int i = tid; i < hs / 2; i += nt) {
                 const float2 cs = op.rope_tab[(size_t)pos * (hs / 2) + i];
                 half* q = op.q + (size_t)h * hs;
-                const float q0 = h2f_bits(ld_cg_u16(q + i)), q1 = h2f_bits(ld_cg_u16(q + i + hs / 2));
+                const half* kr = op.kraw + (size_t)kvh * hs;
+                const uint32_t q0b = ld_cg_u16(q + i), q1b = ld_cg_u16(q + i + hs / 2), k0b = ld_cg_u16(kr + i), k1b = ld_cg_u16(kr + i + hs / 2);
+                const float q0 = h2f_bits(q0b), q1 = h2f_bits(q1b), k0 = h2f_bits(k0b), k1 = h2f_bits(k1b);
                 const half o0 = __float2half_rn(__fmaf_rn(q0, cs.x, -__fmul_rn(q1, cs.y)));
                 const half o1 = __float2half_rn(__fmaf_rn(q1, cs.x, __fmul_rn(q0, cs.y)));
                 q[i] = o0; q[i + hs / 2] = o1;
                 qs[i] = __half2float(o0); qs[i + hs / 2] = __half2float(o1);
-                const half* kr = op.kraw + (size_t)kvh * hs;
-                const float k0 = h2f_bits(ld_cg_u16(kr + i)), k1 = h2f_bits(ld_cg_u16(kr + i + hs / 2));
                 const half r0 = __float2half_rn(__fmaf_rn(k0, cs.x, -__fmul_rn(k1, cs.y)));
                 const half r1 = __float2half_rn(__fmaf_rn(k0, cs.y, __fmul_rn(k1, cs.x)));
                 krow[i] = __half2float(r0); krow[i + hs / 2] = __half2float(r1);
@@ -848,57 +897,48 @@ __device__ void run_attn_t(Ctx& c, const Op& op) {
                     kd[i] = r0; kd[i + hs / 2] = r1;
                 }
             }
+            for (int i = tid - 64; i >= 0 && i < hs; i += nt) vrow[i] = h2f_bits(ld_cg_u16(vbase + (size_t)pos * op.kv_stride + i));
         } else {
             for (int i = tid; i < hs; i += nt) {
                 qs[i] = h2f_bits(ld_cg_u16(op.q + (size_t)h * hs + i));
                 krow[i] = h2f_bits(ld_cg_u16(kbase + (size_t)pos * op.kv_stride + i));
+                vrow[i] = h2f_bits(ld_cg_u16(vbase + (size_t)pos * op.kv_stride + i));
             }
         }
-        named_bar(kBarAll, nt);
-        trace_mark(c, 2);
-        // ---- scores: one warp per t (lane chain over j = 32 i + lane, gpu_kernels.h:154-159) ----
-        // Rows are taken eight at a time with every load issued before the first use: one trip to L2 per batch.
-        const int nser = hs / 32;
-        if (NSER > 0) {
-            constexpr int TB = 8, NS = NSER > 0 ? NSER : 1;
-            for (int tb = warp; tb < size; tb += TB * c.nwc) {
-                uint32_t kv[TB][NS];
-#pragma unroll
-                for (int u = 0; u < TB; u++) {
-                    const int t = tb + u * c.nwc;
-                    const half* kr = kbase + (size_t)t * op.kv_stride;
-#pragma unroll
-                    for (int i = 0; i < NS; i++) kv[u][i] = (t < pos) ? ld_cg_u16(kr + i * 32 + lane) : 0u;
-                }
-#pragma unroll
-                for (int u = 0; u < TB; u++) {
-                    const int t = tb + u * c.nwc;
-                    float sum = 0.0f;
-#pragma unroll
-                    for (int i = 0; i < NS; i++) {
-                        const float kval = (t == pos) ? krow[i * 32 + lane] : h2f_bits(kv[u][i]);
-                        sum = __fmaf_rn(kval, qs[i * 32 + lane], sum);
-                    }
-                    sum = warp_tree_sum(sum);
-                    sum = __fmul_rn(sum, op.att_alpha);
-                    if (lane == 0 && t < size) att[t] = __half2float(__float2half_rn(sum));
-                }
+        if (tid < 64 && nt <= 64) for (int i = tid; i < hs; i += nt) vrow[i] = h2f_bits(ld_cg_u16(vbase + (size_t)pos * op.kv_stride + i));
+        // ---- scores (lane chain over j = 32 i + lane, gpu_kernels.h:154-159), K tile by tile ----
+#pragma unroll 1
+        for (int tile0 = 0; tile0 < pos; tile0 += kAttnTile) {
+            const int nrows = (pos - tile0 < kAttnTile) ? pos - tile0 : kAttnTile;
+            if (!(have_tile0 && tile0 == 0)) {
+                named_bar(kBarAll, nt);                    // the previous tile is no longer read
+                attn_load_tile(c, bufA, kbase, op.kv_stride, hs, tile0, nrows);
             }
-        } else {
-            for (int t = warp; t < size; t += c.nwc) {
+            named_bar(kBarAll, nt);                        // tile (and, first time round, qs / krow / vrow) visible
+#pragma unroll 2
+            for (int r = warp; r < nrows; r += c.nwc) {
+                const uint32_t row = bufA + (uint32_t)r * hs * 2;
                 float sum = 0.0f;
-                if (t == pos) {
-                    for (int i = 0; i < nser; i++) sum = __fmaf_rn(krow[i * 32 + lane], qs[i * 32 + lane], sum);
-                } else {
-                    const half* kr = kbase + (size_t)t * op.kv_stride;
-                    for (int i = 0; i < nser; i++)
-                        sum = __fmaf_rn(h2f_bits(ld_cg_u16(kr + i * 32 + lane)), qs[i * 32 + lane], sum);
-                }
+#pragma unroll
+                for (int i = 0; i < NS; i++) sum = __fmaf_rn(h2f_bits(lds_u16(row + (i * 32 + lane) * 2)), qs[i * 32 + lane], sum);
                 sum = warp_tree_sum(sum);
                 sum = __fmul_rn(sum, op.att_alpha);
-                if (lane == 0) att[t] = __half2float(__float2half_rn(sum));
+                if (lane == 0) att[tile0 + r] = __half2float(__float2half_rn(sum));
             }
         }
+        if (pos == 0 || true) named_bar(kBarAll, nt);      // krow visible (pos == 0: no tile loop ran); all tile reads done
+        if (warp == 0) {                                   // the row of this step
+            float sum = 0.0f;
+#pragma unroll
+            for (int i = 0; i < NS; i++) sum = __fmaf_rn(krow[i * 32 + lane], qs[i * 32 + lane], sum);
+            sum = warp_tree_sum(sum);
+            sum = __fmul_rn(sum, op.att_alpha);
+            if (lane == 0) att[pos] = __half2float(__float2half_rn(sum));
+        }
+        // second V tile (if any) goes to bufA while the softmax runs: K is dead from here on
+        const int v1rows = (pos > kAttnTile) ? ((pos - kAttnTile < kAttnTile) ? pos - kAttnTile : kAttnTile) : 0;
+        if (!have_tile0) attn_load_tile(c, bufB, vbase, op.kv_stride, hs, 0, pos < kAttnTile ? pos : kAttnTile);
+        if (v1rows > 0) attn_load_tile(c, bufA, vbase, op.kv_stride, hs, kAttnTile, v1rows);
         named_bar(kBarAll, nt);
         trace_mark(c, 3);
         // ---- softmax (idle reference threads seed the max with 0, gpu_kernels.h:374) ----
@@ -931,61 +971,47 @@ __device__ void run_attn_t(Ctx& c, const Op& op) {
         }
         named_bar(kBarAll, nt);
         trace_mark(c, 4);
-        // ---- PV: reference lane tx chains t = 32 e + tx (e ascending); then the cub tree over tx ----
-        // A lane owns hs/32 consecutive outputs; the V rows of eight steps of a chain are loaded before the first FMA.
-        if (NSER > 0) {
-            constexpr int EB = 8, NS = NSER > 0 ? NSER : 1;
-            for (int tx = warp; tx < 32; tx += c.nwc) {
-                float a[NS];
+        // ---- PV: reference lane tx chains t = 32 e + tx (e ascending); then the cub tree over tx.  A warp keeps the
+        // chains of up to four tx (tx = warp + k * nwc); a lane owns hs/32 consecutive outputs. ----
+        float a[4][NS];
 #pragma unroll
-                for (int q = 0; q < NS; q++) a[q] = 0.0f;
-                for (int t0 = tx; t0 < size; t0 += 32 * EB) {
-                    uint32_t vv[EB][(NS + 1) / 2];
+        for (int k = 0; k < 4; k++)
 #pragma unroll
-                    for (int e = 0; e < EB; e++) {
-                        const int t = t0 + 32 * e;
-                        const half* vr = vbase + (size_t)t * op.kv_stride + lane * NS;
-#pragma unroll
-                        for (int q2 = 0; q2 < (NS + 1) / 2; q2++) vv[e][q2] = 0u;
-                        if (t < size) {
-                            if (NS == 4) { const uint2 r = ld_cg_v2(vr); vv[e][0] = r.x; vv[e][1] = r.y; }
-                            else if (NS == 8) { const uint4 r = ld_cg_v4(vr); vv[e][0] = r.x; vv[e][1] = r.y; vv[e][2] = r.z; vv[e][3] = r.w; }
-                            else if (NS == 2) { asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(vv[e][0]) : "l"(vr)); }
-                            else vv[e][0] = ld_cg_u16(vr);
-                        }
-                    }
-#pragma unroll
-                    for (int e = 0; e < EB; e++) {
-                        const int t = t0 + 32 * e;
-                        if (t < size) {
-                            const float pt = att[t];
-#pragma unroll
-                            for (int q = 0; q < NS; q++) {
-                                const uint32_t word = vv[e][q >> 1];
-                                a[q] = __fmaf_rn(h2f_bits((q & 1) ? (word >> 16) : (word & 0xFFFFu)), pt, a[q]);
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < NS; q++) part[tx * hs + lane * NS + q] = a[q];
+            for (int q = 0; q < NS; q++) a[k][q] = 0.0f;
+#pragma unroll 1
+        for (int tile0 = 0, ti = 0; tile0 < pos; tile0 += kAttnTile, ti++) {
+            const int nrows = (pos - tile0 < kAttnTile) ? pos - tile0 : kAttnTile;
+            const uint32_t buf = (ti & 1) ? bufA : bufB;   // tile 0 in bufB, tile 1 in bufA, then alternating
+            if (ti >= 2) {
+                named_bar(kBarAll, nt);
+                attn_load_tile(c, buf, vbase, op.kv_stride, hs, tile0, nrows);
+                named_bar(kBarAll, nt);
             }
-        } else {
-            const int per_lane = hs / 32;
-            for (int tx = warp; tx < 32; tx += c.nwc) {
-                float a[8];
 #pragma unroll
-                for (int q = 0; q < 8; q++) a[q] = 0.0f;
-                for (int t = tx; t < size; t += 32) {
-                    const half* vr = vbase + (size_t)t * op.kv_stride + lane * per_lane;
-                    const float pt = att[t];
+            for (int k = 0; k < 4; k++) {
+                const int tx = warp + k * c.nwc;
+                if (tx < 32) {
+                    for (int t = tile0 + tx; t < tile0 + nrows; t += 32) {     // kAttnTile % 32 == 0: t % 32 == tx
+                        const float pt = att[t];
+                        const uint32_t row = buf + (uint32_t)(t - tile0) * hs * 2 + lane * NS * 2;
 #pragma unroll
-                    for (int q = 0; q < 8; q++)
-                        if (q < per_lane) a[q] = __fmaf_rn(h2f_bits(ld_cg_u16(vr + q)), pt, a[q]);
+                        for (int q = 0; q < NS; q++) a[k][q] = __fmaf_rn(h2f_bits(lds_u16(row + q * 2)), pt, a[k][q]);
+                    }
+                }
+            }
+        }
+        named_bar(kBarAll, nt);                            // tiles are dead: `part` may overwrite bufA
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int tx = warp + k * c.nwc;
+            if (tx < 32) {
+                if ((pos & 31) == tx) {                    // the row of this step closes its chain
+                    const float pt = att[pos];
+#pragma unroll
+                    for (int q = 0; q < NS; q++) a[k][q] = __fmaf_rn(vrow[lane * NS + q], pt, a[k][q]);
                 }
 #pragma unroll
-                for (int q = 0; q < 8; q++)
-                    if (q < per_lane) part[tx * hs + lane * per_lane + q] = a[q];
+                for (int q = 0; q < NS; q++) part[tx * hs + lane * NS + q] = a[k][q];
             }
         }
         named_bar(kBarAll, nt);
@@ -1005,10 +1031,12 @@ __device__ void run_attn_t(Ctx& c, const Op& op) {
     }
 }
 
-__device__ void run_attn(Ctx& c, const Op& op) {
-    if (op.head_size == 128) run_attn_t<4>(c, op);
-    else if (op.head_size == 64) run_attn_t<2>(c, op);
-    else run_attn_t<0>(c, op);
+__device__ void run_attn(Ctx& c, const Op& op, bool prefetched) {
+    switch (op.head_size) {            // the host accepts only these head sizes for the persistent kernel
+        case 128: run_attn_t<4>(c, op, prefetched); break;
+        case 64: run_attn_t<2>(c, op, prefetched); break;
+        default: run_attn_t<1>(c, op, prefetched); break;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1022,6 +1050,7 @@ __device__ void run_argmax(Ctx& c, const Op& op, int write_token) {
     int max_pos = 0x7fffffff;
     // 8 logits per 16-byte load, four loads in flight per thread; ascending index order per thread keeps "first maximum"
     const int nvec = op.vocab >> 3;
+#pragma unroll 1
     for (int vb = c.ctid; vb < nvec; vb += 4 * c.nthreads) {
         uint4 lv[4];
 #pragma unroll
@@ -1066,7 +1095,7 @@ __device__ void run_argmax(Ctx& c, const Op& op, int write_token) {
 // ------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512, 1) interp_kernel(const __grid_constant__ InterpParams P) {
+__global__ void __launch_bounds__(32 * (kMaxConsumerWarps + 1), 1) interp_kernel(const __grid_constant__ InterpParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const Op* ops = (P.ops != nullptr) ? P.ops : &P.one;
@@ -1122,6 +1151,8 @@ __global__ void __launch_bounds__(512, 1) interp_kernel(const __grid_constant__ 
         c.meta_pending = -1;
         NormRegs nr;
         load_norm_regs(c, ops[o], nr);             // in flight while the grid barrier completes
+        const bool attn_pref = (ops[o].kind == OP_ATTN) && sync_before;
+        if (attn_pref) attn_prefetch(c, ops[o]);   // K / V rows of earlier positions do not depend on it either
         if (sync_before) {
             c.nsync++;
             if (c.ctid == 0) grid_wait(P.sync, c.nsync * gridDim.x);
@@ -1133,7 +1164,7 @@ __global__ void __launch_bounds__(512, 1) interp_kernel(const __grid_constant__ 
             case OP_GEMV:
             case OP_FFN: run_q4(c, op, nr); break;
             case OP_CLS: run_cls(c, op, nr); break;
-            case OP_ATTN: run_attn(c, op); break;
+            case OP_ATTN: run_attn(c, op, attn_pref); break;
             case OP_ARGMAX: run_argmax(c, op, (P.write_token >= 0) ? P.write_token : op.write_token); break;
             default: break;
         }

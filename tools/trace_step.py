@@ -54,5 +54,5 @@ ph = np.array([[ts[2048 + b * 8 + k] for k in range(8)] for b in range(nb)], dty
 t0 = ph[:, 1].min()
 rel = (ph - t0) / 1000.0
 print(f"op {trace_op} ({names[kinds[trace_op] // 100000]} K={kinds[trace_op] % 100000}) phases in us relative to the first CTA past the barrier [min / median / max over CTAs]:")
-for k, name in enumerate(["arrive(prev done)", "barrier passed", "x staged", "first weights", "warp0 done", "all warps done", "raw x in smem", "rms scale known"]):
+for k, name in enumerate(["arrive(prev done)", "barrier passed", "x staged", "first weights", "warp0 done", "all warps done", "warp0 task 1 done", "warp0 task 2 done"]):
     print(f"  {name:18s} {rel[:, k].min():8.2f} {np.median(rel[:, k]):8.2f} {rel[:, k].max():8.2f}")
