@@ -240,7 +240,8 @@ bool cls_op_shape(Op& op, int n, int d, int row_stride) {
     op.T = (n + 255) / 256;
     op.nseg = 1;
     op.seg[0].ncols = d;
-    op.ntasks = (d + 3) / 4;
+    op.rpt = (n * 2 >= 4096) ? 1 : 4;     // a long row alone keeps a warp busy and takes one ring slot instead of four
+    op.ntasks = (d + op.rpt - 1) / op.rpt;
     op.au = 1;
     op.row_stride = row_stride;
     return true;
@@ -251,10 +252,11 @@ int op_min_chunk(const Op& op) {
     return (op.kind == OP_FFN ? 2 : 1) * q4_col_bytes(op.K);
 }
 // bytes of a whole warp-task (4 columns | 2 gate/up pairs | 4 rows)
-int op_task_bytes(const Op& op) { return op_min_chunk(op) * (op.kind == OP_FFN ? 2 : 4); }
+int op_task_chunks(const Op& op) { return op.kind == OP_FFN ? 2 : op.kind == OP_CLS ? op.rpt : 4; }
+int op_task_bytes(const Op& op) { return op_min_chunk(op) * op_task_chunks(op); }
 // cut the op's tasks into ring slots of `slot` bytes
 bool op_set_chunking(Op& op, int slot) {
-    const int per = op.kind == OP_FFN ? 2 : 4;      // chunks of minimum size per task
+    const int per = op_task_chunks(op);             // chunks of minimum size per task
     int cps = per;
     while (cps >= 1 && cps * op_min_chunk(op) > slot) cps >>= 1;
     if (cps < 1) return false;

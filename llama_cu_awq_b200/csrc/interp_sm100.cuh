@@ -61,6 +61,7 @@ struct Op {
     int T;                 // trips: ceil(K / 1024)  (OP_CLS: ceil(n / 256))
     int cps;               // columns (gate/up pairs, rows) per ring slot: 4, 2 or 1
     int spt;               // ring slots per warp-task
+    int rpt;               // OP_CLS: rows per warp-task (4, or 1 when a row is long enough to keep a warp busy)
     int au;                // CTA task ranges start on multiples of `au` tasks (16-byte alignment of the scale/zero copies)
     int ntasks;            // warp-tasks of the whole op (4 columns | 2 gate/up pairs | 4 rows each)
     int nseg;
@@ -365,7 +366,7 @@ __device__ void producer_loop(const InterpParams& P, const Op* ops, const Smem& 
                     bulk_g2s(dst, (const uint8_t*)op.seg[0].w + off, bytes, bar, policy);
                     bulk_g2s(dst + bytes, (const uint8_t*)op.seg[1].w + off, bytes, bar, policy);
                 } else {
-                    const int row = task * 4 + i * cps;
+                    const int row = task * op.rpt + i * cps;
                     int rows = op.seg[0].ncols - row;
                     if (rows > cps) rows = cps;
                     if (rows < 0) rows = 0;
@@ -645,13 +646,14 @@ __device__ void run_q4(Ctx& c, const Op& op, const NormRegs& nr) {
 
     mbar_wait(c.sm.mfull(mb), (c.mcount >> 1) & 1);      // scales / zero points of this op have landed
     const int K = op.K, T = op.T, G = q4_groups(K), zh = q4_zh(K), colb = q4_col_bytes(K);
-    const int cps = op.cps, spt = op.spt;
+    const int cps = op.cps, spt = op.spt, csh = (cps == 4) ? 2 : (cps == 2) ? 1 : 0;
     const bool dual = (op.kind == OP_FFN);
     const int h = c.lane >> 4, j = c.lane & 15, sw = (j >> 2) & 1;
+    const int nseg = op.nseg, ncols0 = op.seg[0].ncols, ncols1 = op.seg[1].ncols;     // read once, not once per task
+    RingPos rp = ring_pos(c, c.qbase + (unsigned)c.warp * spt);                        // this warp's first task
 #pragma unroll 1
     for (int task = t0 + c.warp; task < t1; task += c.nwc) {
         // ---- my two columns: where their weights, scales and zeros are ----
-        RingPos rp = ring_pos(c, c.qbase + (unsigned)(task - t0) * spt);
         int seg = 0, col = 0;
         uint32_t scol0, scol1, zcol0, zcol1, w0, w1;
         // wait for every slot of the task
@@ -667,21 +669,22 @@ __device__ void run_q4(Ctx& c, const Op& op, const NormRegs& nr) {
             // slot: [gate cps columns][up cps columns]; output h of the task is column h % cps of slot h / cps
             RingPos r = rp;
             if (h >= cps) ring_next(c, r);                            // cps == 1: second output sits in the second slot
-            w0 = c.sm.slot(r.slot) + (h % cps) * colb;
+            w0 = c.sm.slot(r.slot) + (h & (cps - 1)) * colb;
             w1 = w0 + cps * colb;
         } else {
             const int ncol = (t1 - t0) * 4, lc = (task - t0) * 4 + 2 * h;  // local index of my first column
-            gemv_locate(op, task * 4, seg, col);
+            col = task * 4;
+            if (nseg > 1 && col >= ncols0) { col -= ncols0; seg = 1; if (nseg > 2 && col >= ncols1) { col -= ncols1; seg = 2; } }
             col += 2 * h;
             scol0 = meta + lc * G * 2;                         scol1 = scol0 + G * 2;
             zcol0 = meta + ncol * G * 2 + lc * zh * 4;         zcol1 = zcol0 + zh * 4;
             // column i (0..3) of the task is column i % cps of slot i / cps
             RingPos r = rp;
             const int i0 = 2 * h, i1 = 2 * h + 1;
-            for (int s = 0; s < i0 / cps; s++) ring_next(c, r);
-            w0 = c.sm.slot(r.slot) + (i0 % cps) * colb;
-            if (i1 / cps != i0 / cps) ring_next(c, r);
-            w1 = c.sm.slot(r.slot) + (i1 % cps) * colb;
+            for (int s = 0; s < (i0 >> csh); s++) ring_next(c, r);
+            w0 = c.sm.slot(r.slot) + (i0 & (cps - 1)) * colb;
+            if ((i1 >> csh) != (i0 >> csh)) ring_next(c, r);
+            w1 = c.sm.slot(r.slot) + (i1 & (cps - 1)) * colb;
         }
         if (task == t0) trace_mark(c, 3);                 // warp 0: first task's weights are in shared memory
         w0 += j * 32 + sw * 16;
@@ -699,6 +702,10 @@ __device__ void run_q4(Ctx& c, const Op& op, const NormRegs& nr) {
         if (c.lane == 0) {
             RingPos r = rp;
             for (int i = 0; i < spt; i++) { ring_release(c, r); ring_next(c, r); }
+        }
+        {   // ring position of this warp's next task: nwc tasks further on
+            rp.slot += c.nwc * spt;
+            while (rp.slot >= c.sm.S) { rp.slot -= c.sm.S; rp.lap++; }
         }
         if (task == t0) trace_mark(c, 6);                 // warp 0: first task done
         else if (task == t0 + c.nwc) trace_mark(c, 7);    // warp 0: second task done
@@ -768,8 +775,8 @@ __device__ void run_cls(Ctx& c, const Op& op, const NormRegs& nr) {
     cta_task_range(op, blockIdx.x, gridDim.x, t0, t1);
 #pragma unroll 1
     for (int task = t0 + c.warp; task < t1; task += c.nwc) {
-        int rows = op.seg[0].ncols - task * 4;
-        if (rows > 4) rows = 4;
+        int rows = op.seg[0].ncols - task * op.rpt;
+        if (rows > op.rpt) rows = op.rpt;
         const RingPos rp = ring_pos(c, c.qbase + (unsigned)(task - t0) * spt);
         uint32_t wrow[4];
         {
@@ -809,7 +816,7 @@ __device__ void run_cls(Ctx& c, const Op& op, const NormRegs& nr) {
         const float tot = warp_tree_sum4(acc[0], acc[1], acc[2], acc[3], lane);   // lanes 0,1,2,3 hold rows 0,2,1,3
         if (lane < 4) {
             const int r = 2 * (lane & 1) + ((lane >> 1) & 1);
-            if (r < rows) op.seg[0].out[task * 4 + r] = __float2half_rn(__fmul_rn(tot, op.alpha));
+            if (r < rows) op.seg[0].out[task * op.rpt + r] = __float2half_rn(__fmul_rn(tot, op.alpha));
         }
     }
     c.qbase += (unsigned)(t1 - t0) * spt;
