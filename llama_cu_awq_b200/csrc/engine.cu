@@ -15,6 +15,10 @@
 #include <string>
 #include <vector>
 
+#include <float.h>
+
+#include <cub/cub.cuh>
+
 #include "lq4_types.h"
 #include "kernels_sm100.cuh"
 #include "interp_sm100.cuh"
@@ -334,6 +338,63 @@ void run_single(Op& op, const int* pPos) {
     }
     if (!make_plan(pl, default_nwc(), xs, meta, slot)) unsupported();
     launch_interp(pl, nullptr, 1, &op, pPos, -1, false, grid);
+}
+
+// ------------------------------------------------------------------------------- temperature / top-p sampler
+// Off the hot path (the metric is greedy): the reference's pipeline (sampler.h:51-81) restated with the same
+// library calls -- cub::DeviceRadixSort / cub::DeviceScan from the toolkit both builds use -- so that a fixed
+// seed gives the reference's tokens.  All probabilities live in fp16, including the prefix sum.
+__global__ void __launch_bounds__(1024) softmax_logits_kernel(half* logits, int size, float temperature, int* indices) {
+    // gpu_kernels.h:499-550: divide by the temperature (fp16 round trip), softmax in fp16 storage, indices[t] = t
+    const int tid = threadIdx.x, step = blockDim.x;
+    for (int t = tid; t < size; t += step) {
+        indices[t] = t;
+        float val = __half2float(logits[t]);
+        val = __fdiv_rn(val, temperature);
+        logits[t] = __float2half_rn(val);
+    }
+    __syncthreads();
+    using BlockReduce = cub::BlockReduce<float, 1024>;
+    __shared__ typename BlockReduce::TempStorage temp;
+    __shared__ float shared_val;
+    float max_val = tid < size ? __half2float(logits[tid]) : -FLT_MAX;
+    for (int i = tid + step; i < size; i += step)
+        if (__half2float(logits[i]) > max_val) max_val = __half2float(logits[i]);
+    max_val = BlockReduce(temp).Reduce(max_val, cub::Max());
+    if (tid == 0) shared_val = max_val;
+    __syncthreads();
+    max_val = shared_val;
+    float sum = 0.0f;
+    for (int i = tid; i < size; i += step) {
+        const float v = expf(__fsub_rn(__half2float(logits[i]), max_val));
+        logits[i] = __float2half_rn(v);
+        sum = __fadd_rn(sum, v);
+    }
+    __syncthreads();                       // temp is reused
+    sum = BlockReduce(temp).Sum(sum);
+    if (tid == 0) shared_val = sum;
+    __syncthreads();
+    sum = shared_val;
+    for (int t = tid; t < size; t += step) logits[t] = __float2half_rn(__fdiv_rn(__half2float(logits[t]), sum));
+}
+
+__global__ void __launch_bounds__(1024) sample_top_p_kernel(const half* prefix_sum, const int* indices, int n, float threshold, int* result,
+                                                            volatile int* pPos, int* pPosGpu) {
+    // gpu_kernels.h:555-584: first position whose fp16 prefix sum reaches the threshold (n-1 when none does)
+    const int tid = threadIdx.x, step = blockDim.x;
+    int min_index = n - 1;
+    for (int t = tid; t < n; t += step)
+        if (__half2float(prefix_sum[t]) >= threshold && t < min_index) min_index = t;
+    using BlockReduce = cub::BlockReduce<int, 1024>;
+    __shared__ typename BlockReduce::TempStorage temp;
+    const int min_index_global = BlockReduce(temp).Reduce(min_index, cub::Min());
+    if (tid == 0) {
+        int token_pos = *pPos;
+        token_pos++;
+        result[token_pos] = indices[min_index_global];
+        *pPos = token_pos;
+        *pPosGpu = token_pos;
+    }
 }
 
 }  // namespace
@@ -725,29 +786,51 @@ static unsigned int random_u32(unsigned long long* state) {   // sampler.h:31-37
     return (unsigned int)((*state * 0x2545F4914F6CDD1Dull) >> 32);
 }
 
-static void check_greedy(Sampler* sampler, int gen_token) {
-    if (sampler->temperature != 0.0f && gen_token) {
-        // temperature / top-p sampling (sampler.h:51-81) is scope row f3: not built yet, fail loudly
-        fprintf(stderr, "lq4: only greedy sampling (-t 0) is implemented\n");
-        exit(EXIT_FAILURE);
+static float random_f32(unsigned long long* state) { return (random_u32(state) >> 8) / 16777216.0f; }   // sampler.h:38-40
+
+static bool is_greedy(const Sampler* sampler, int gen_token) { return sampler->temperature == 0.0f || !gen_token; }
+
+// the non-greedy branch of sample() (sampler.h:51-80) with an already drawn coin
+static void sample_nongreedy(Sampler* sampler, RunState* s, float coin, cudaStream_t st) {
+    const int n = sampler->vocab_size;
+    softmax_logits_kernel<<<1, 1024, 0, st>>>(s->logits, n, sampler->temperature, sampler->indices);
+    float threshold = 0.0f;
+    if (sampler->topp <= 0 || sampler->topp >= 1) {
+        threshold = coin;
+    } else {
+        if (sampler->temp_storage_bytes_sort == 0) {
+            cub::DeviceRadixSort::SortPairsDescending(sampler->tempStorage_sort, sampler->temp_storage_bytes_sort, s->logits, s->logits,
+                                                      sampler->indices, sampler->indices, n, 0, sizeof(half) * 8, st);
+            LQ4_CHECK(cudaMalloc(&sampler->tempStorage_sort, sampler->temp_storage_bytes_sort));
+        }
+        cub::DeviceRadixSort::SortPairsDescending(sampler->tempStorage_sort, sampler->temp_storage_bytes_sort, s->logits, s->logits,
+                                                  sampler->indices, sampler->indices, n, 0, sizeof(half) * 8, st);
+        threshold = coin * sampler->topp;
     }
+    if (sampler->temp_storage_bytes_scan == 0) {
+        cub::DeviceScan::InclusiveSum(sampler->tempStorage_scan, sampler->temp_storage_bytes_scan, s->logits, s->logits, n, st);
+        LQ4_CHECK(cudaMalloc(&sampler->tempStorage_scan, sampler->temp_storage_bytes_scan));
+    }
+    cub::DeviceScan::InclusiveSum(sampler->tempStorage_scan, sampler->temp_storage_bytes_scan, s->logits, s->logits, n, st);
+    sample_top_p_kernel<<<1, 1024, 0, st>>>(s->logits, sampler->indices, n, threshold, &(s->shared_data->tokens[0]), &(s->shared_data->pos), s->pos);
 }
 
 void lq4_sample(Sampler* sampler, RunState* s, int gen_token, void* cuda_stream) {
     ensure_init();
-    (void)random_u32(&sampler->rng_state);   // the reference burns one draw per step (sampler.h:45)
-    check_greedy(sampler, gen_token);
-    argmax_kernel<<<1, 1024, 0, (cudaStream_t)cuda_stream>>>(s->logits, sampler->vocab_size,
-                                                             &(s->shared_data->tokens[0]), &(s->shared_data->pos),
-                                                             s->pos, nullptr, gen_token != 0);
+    const float coin = random_f32(&sampler->rng_state);   // one draw per step, greedy or not (sampler.h:45)
+    if (is_greedy(sampler, gen_token)) {
+        argmax_kernel<<<1, 1024, 0, (cudaStream_t)cuda_stream>>>(s->logits, sampler->vocab_size, &(s->shared_data->tokens[0]),
+                                                                 &(s->shared_data->pos), s->pos, nullptr, gen_token != 0);
+    } else {
+        sample_nongreedy(sampler, s, coin, (cudaStream_t)cuda_stream);
+    }
 }
 
 // forward + sample; seq_len_bin only matters to the op-by-op path
 static void forward_and_sample(int gen_token, Config* p, RunState* s, TransformerWeights* w, int copyLogits,
                                Sampler* pSampler, int seq_len_bin) {
-    if (g.opt_fused && !copyLogits) {
-        check_greedy(pSampler, gen_token);
-        if (run_network_fused(s->pos, p, s, w, true, gen_token != 0)) {
+    if (g.opt_fused && !copyLogits && is_greedy(pSampler, gen_token)) {
+        if (run_network_fused(s->pos, p, s, w, true, gen_token != 0)) {      // greedy sampler = last op of the persistent kernel
             (void)random_u32(&pSampler->rng_state);
             return;
         }

@@ -78,6 +78,12 @@ int ref_open(const char* bin_path) {
     return 0;
 }
 void ref_config(int* out8) { memcpy(out8, &g_ref_t.config, sizeof(Config)); }
+// switch the stock sampler to temperature / top-p sampling with a fixed seed (main() does this from -t -p -s)
+void ref_set_sampler(float temperature, float topp, unsigned long long seed) {
+    g_ref_sampler.temperature = temperature;
+    g_ref_sampler.topp = topp;
+    g_ref_sampler.rng_state = seed;
+}
 // start a sequence: tokens become the prompt (generate(), llama2_q4.cu:461-463)
 void ref_reset(const int* tokens, int n) {
     cudaMemset(g_ref_t.state.pos, 0, sizeof(int));

@@ -145,6 +145,7 @@ def ref():
         r.ref_open.restype = C.c_int
         r.ref_open.argtypes = [C.c_char_p]
         r.ref_config.argtypes = [P]
+        r.ref_set_sampler.argtypes = [C.c_float, C.c_float, C.c_ulonglong]
         r.ref_reset.argtypes = [P, C.c_int]
         r.ref_step.restype = C.c_int
         r.ref_step.argtypes = [C.c_int, P, P]

@@ -158,3 +158,36 @@ def test_generate_tokens_host_api(eng):
             assert toks[1:steps] == outs[0]
         finally:
             lib.lq4_free_transformer(C.byref(t))
+
+
+@pytest.mark.parametrize("temperature,topp", [(0.8, 0.9), (1.0, 1.0), (0.5, 0.6)])
+def test_sampling_matches_reference(eng, temperature, topp):
+    """Temperature / top-p sampling (sampler.h:51-81, scope row f3): same seed, same model -> the reference's tokens.
+    The pipeline (fp16 softmax, cub radix sort, fp16 cub prefix sum, threshold search) is restated with the same
+    toolkit library calls, and the host xorshift RNG is the reference's."""
+    E, lib = eng
+    r = H.ref()
+    if r is None:
+        pytest.skip("oracle/_ref/libq4ref.so not built")
+    cfg = H.SMALL
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "m.bin")
+        write_model(E, lib, cfg, 4321, path)
+        t = E.Transformer()
+        assert lib.lq4_build_transformer(C.byref(t), path.encode(), 0) == 0
+        s = E.Sampler()
+        lib.lq4_build_sampler(C.byref(s), cfg["vocab_size"], temperature, topp, 777)
+        assert r.ref_open(path.encode()) == 0
+        try:
+            r.ref_set_sampler(temperature, topp, 777)
+            prompt, n_steps, vocab = [1, 35, 72], 48, cfg["vocab_size"]
+            _, ref_toks = run_steps(lambda g, l, n: r.ref_step(g, l, n), r.ref_reset, prompt, n_steps, vocab, True)
+            _, my_toks = run_steps(lambda g, l, n: lib.lq4_step(C.byref(t), C.byref(s), g, l, n),
+                                   lambda p, n: lib.lq4_reset(C.byref(t), C.cast(p, C.POINTER(C.c_int)), n),
+                                   prompt, n_steps, vocab, True)
+            assert my_toks == ref_toks
+            assert len(set(my_toks[3:])) > 4, "sampling should not collapse to one token"
+        finally:
+            r.ref_close()
+            lib.lq4_destroy_sampler(C.byref(s))
+            lib.lq4_free_transformer(C.byref(t))
