@@ -127,7 +127,7 @@ void lq4_run_llama_network(int* pPos, Config* p, RunState* s, TransformerWeights
 /* run_transformer, llama2_q4.cu:346-395: graph-cached forward + sample.  NOT capture-safe (it captures). */
 void lq4_run_transformer(int gen_token, Config* p, RunState* s, TransformerWeights* w, int copyLogits,
                          Sampler* pSampler);
-/* build_sampler / sample, sampler.h:15-23,43-81 (greedy path here; temperature/top-p is row f3) */
+/* build_sampler / sample, sampler.h:15-23,43-81: greedy argmax, or temperature + top-p with the reference's cub pipeline */
 void lq4_build_sampler(Sampler* sampler, int vocab_size, float temperature, float topp,
                        unsigned long long rng_seed);
 void lq4_destroy_sampler(Sampler* sampler);

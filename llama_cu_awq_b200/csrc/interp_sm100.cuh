@@ -404,6 +404,9 @@ struct Ctx {
     unsigned nsync;           // grid barriers taken so far
     unsigned long long* tr;   // detailed phase trace of the current op (this CTA's 8 entries) or nullptr
 };
+__device__ __forceinline__ void cyc_mark(const Ctx& c, int k) {      // SM clock, warp 0 lane 0: sub-microsecond phases
+    if (c.tr != nullptr && c.lane == 0 && c.warp == 0) (c.tr - blockIdx.x * 8 + 148 * 8 + blockIdx.x * 16)[k] = (unsigned long long)clock64();
+}
 __device__ __forceinline__ void trace_mark(const Ctx& c, int k) {
     if (c.tr != nullptr && c.lane == 0 && (c.warp == 0 || k >= 8)) c.tr[k & 7] = global_ns();
 }
@@ -482,7 +485,10 @@ __device__ float stage_raw_and_scale(Ctx& c, const Op& op, const half* xin, uint
         if (op.emb != nullptr && blockIdx.x == 0 && op.x_copy != nullptr) *reinterpret_cast<uint4*>(op.x_copy + u * 8) = xv;
     }
     named_bar(kBarAll, c.nthreads);
-    return cta_rms_scale(c, xraw, K);
+    cyc_mark(c, 1);                               // raw x and norm weights in shared memory
+    const float scale = cta_rms_scale(c, xraw, K);
+    cyc_mark(c, 2);                               // scale known
+    return scale;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -643,8 +649,10 @@ __device__ void run_q4(Ctx& c, const Op& op, const NormRegs& nr) {
     const int mb = c.mcount & 1;
     const uint32_t meta = c.sm.mbuf(mb);
     trace_mark(c, 2);                                    // activations staged
+    cyc_mark(c, 3);
 
     mbar_wait(c.sm.mfull(mb), (c.mcount >> 1) & 1);      // scales / zero points of this op have landed
+    cyc_mark(c, 4);
     const int K = op.K, T = op.T, G = q4_groups(K), zh = q4_zh(K), colb = q4_col_bytes(K);
     const int cps = op.cps, spt = op.spt, csh = (cps == 4) ? 2 : (cps == 2) ? 1 : 0;
     const bool dual = (op.kind == OP_FFN);
@@ -686,7 +694,7 @@ __device__ void run_q4(Ctx& c, const Op& op, const NormRegs& nr) {
             if ((i1 >> csh) != (i0 >> csh)) ring_next(c, r);
             w1 = c.sm.slot(r.slot) + (i1 & (cps - 1)) * colb;
         }
-        if (task == t0) trace_mark(c, 3);                 // warp 0: first task's weights are in shared memory
+        if (task == t0) { trace_mark(c, 3); cyc_mark(c, 5); }   // warp 0: first task's weights are in shared memory
         w0 += j * 32 + sw * 16;
         w1 += j * 32 + sw * 16;
         unsigned long long acc0 = 0ull, acc1 = 0ull;
@@ -707,7 +715,7 @@ __device__ void run_q4(Ctx& c, const Op& op, const NormRegs& nr) {
             rp.slot += c.nwc * spt;
             while (rp.slot >= c.sm.S) { rp.slot -= c.sm.S; rp.lap++; }
         }
-        if (task == t0) trace_mark(c, 6);                 // warp 0: first task done
+        if (task == t0) { trace_mark(c, 6); cyc_mark(c, 6); }   // warp 0: first task done
         else if (task == t0 + c.nwc) trace_mark(c, 7);    // warp 0: second task done
         // ---- epilogue ----
         const float v0 = halfwarp_total(acc0), v1 = halfwarp_total(acc1);
@@ -1151,6 +1159,7 @@ __global__ void __launch_bounds__(32 * (kMaxConsumerWarps + 1), 1) interp_kernel
         trace_mark(c, 5);                          // previous op: every warp of this CTA is done
         c.tr = (P.trace != nullptr && o == P.trace_op) ? P.trace + 2048 + blockIdx.x * 8 : nullptr;
         trace_mark(c, 0);                          // this CTA arrives at the op
+        cyc_mark(c, 7);
         if (c.ctid == 0) {
             if (c.meta_pending >= 0) mbar_arrive(sm.mempty(c.meta_pending));
             if (sync_before) grid_arrive(P.sync);
@@ -1167,6 +1176,7 @@ __global__ void __launch_bounds__(32 * (kMaxConsumerWarps + 1), 1) interp_kernel
         named_bar(kBarAll, c.nthreads);
         if (P.trace != nullptr && blockIdx.x == 0 && c.ctid == 0) P.trace[o] = global_ns();
         trace_mark(c, 1);                          // grid barrier passed
+        cyc_mark(c, 0);
         switch (op.kind) {
             case OP_GEMV:
             case OP_FFN: run_q4(c, op, nr); break;

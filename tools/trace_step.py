@@ -29,7 +29,7 @@ lib.lq4_set_option(b"trace_op", trace_op)
 for i in range(npos):
     lib.lq4_enqueue_step(C.byref(t), C.byref(s), i + 1, 1)
 assert lib.lq4_stream_synchronize() == 0
-N = 4096
+N = 8192
 ts = (C.c_ulonglong * N)()
 kinds = (C.c_int * N)()
 n = lib.lq4_debug_trace(ts, kinds, N)
@@ -56,3 +56,10 @@ rel = (ph - t0) / 1000.0
 print(f"op {trace_op} ({names[kinds[trace_op] // 100000]} K={kinds[trace_op] % 100000}) phases in us relative to the first CTA past the barrier [min / median / max over CTAs]:")
 for k, name in enumerate(["arrive(prev done)", "barrier passed", "x staged", "first weights", "warp0 done", "all warps done", "warp0 task 1 done", "warp0 task 2 done"]):
     print(f"  {name:18s} {rel[:, k].min():8.2f} {np.median(rel[:, k]):8.2f} {rel[:, k].max():8.2f}")
+
+cy = np.array([[ts[2048 + 148 * 8 + b * 16 + k] for k in range(8)] for b in range(nb)], dtype=np.float64)
+names_c = ["barrier passed", "raw x staged", "rms scale known", "pairs staged", "meta landed", "first weights", "first task done", "(arrive)"]
+print("  SM-clock phases of warp 0, cycles since 'barrier passed' [median over CTAs] (1965 cycles = 1 us):")
+for k in range(1, 7):
+    print(f"    {names_c[k]:18s} {np.median(cy[:, k] - cy[:, 0]):9.0f}")
+print(f"    arrive -> passed   {np.median(cy[:, 0] - cy[:, 7]):9.0f}")
