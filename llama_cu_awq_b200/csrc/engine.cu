@@ -49,7 +49,8 @@ struct NetPlan {
     Plan plan;
     Op* d_ops = nullptr;
     int nops = 0;              // including the trailing OP_ARGMAX
-    half* kraw = nullptr;      // un-rotated k row of the current step (consumed by OP_ATTN)
+    uint32_t* tagged = nullptr;   // flag-in-data activation vectors of the fused step: x | xb | hb | q | k (un-rotated) | v
+    int opt_tagged = 1;
     std::vector<char> key;     // Config + pointers the table was built from
     bool ok = false;           // false: some shape is not supported by the persistent kernel
 };
@@ -69,6 +70,7 @@ struct Engine {
     std::map<RopeKey, float2*> rope_tabs;
     std::map<const void*, NetPlan> nets;
     unsigned* sync = nullptr;
+    unsigned long long launch_seq = 1;   // persistent-kernel launches so far (activation tags)
     int opt_trace = 0;      // record per-op timestamps of fused steps (development aid)
     int opt_trace_op = -1;  // op whose phases are recorded per CTA
     unsigned long long* trace = nullptr;
@@ -281,9 +283,9 @@ int op_meta_bytes(const Op& op, int grid) {
     return cols * (q4_groups(op.K) * 2 + q4_zh(op.K) * 4) + 64;
 }
 
-void set_seg(Seg& sg, const QWeight* w, half* out, int ncols, int loff, int pos_stride) {
+void set_seg(Seg& sg, const QWeight* w, half* out, int ncols, int loff, int pos_stride, uint32_t* out32 = nullptr) {
     sg.w = w->weight; sg.z = w->zeros; sg.s = reinterpret_cast<const uint16_t*>(w->scales);
-    sg.out = out; sg.ncols = ncols; sg.loff = loff; sg.pos_stride = pos_stride; sg.pad_ = 0;
+    sg.out = out; sg.out32 = out32; sg.ncols = ncols; sg.loff = loff; sg.pos_stride = pos_stride; sg.pad_ = 0;
 }
 
 void launch_interp(const Plan& pl, const Op* d_ops, int nops, const Op* one, const int* pPos, int write_token,
@@ -294,6 +296,7 @@ void launch_interp(const Plan& pl, const Op* d_ops, int nops, const Op* one, con
     P.nwc = pl.nwc; P.nslots = pl.nslots; P.slot_bytes = pl.slot_bytes; P.meta_bytes = pl.meta_bytes; P.xs_bytes = pl.xs_bytes;
     P.write_token = write_token;
     P.sync = g.sync; P.pPos = pPos;
+    P.seq_base = (unsigned)((g.launch_seq++ * (unsigned long long)std::max(nops, 1)) & 0x3FFFFFFFull);
     if (g.opt_trace && d_ops != nullptr && nops + 1 <= 2048) {
         if (!g.trace) { LQ4_CHECK(cudaMalloc((void**)&g.trace, 8192 * sizeof(unsigned long long))); LQ4_CHECK(cudaMemset(g.trace, 0, 8192 * sizeof(unsigned long long))); }
         P.trace = g.trace;
@@ -428,7 +431,7 @@ const char* lq4_last_error(void) { return g.err; }
 int lq4_sm_count(void) { ensure_init(); return g.sm_count; }
 
 static void drop_net_plans() {
-    for (auto& kv : g.nets) { cudaFree(kv.second.d_ops); cudaFree(kv.second.kraw); }
+    for (auto& kv : g.nets) { cudaFree(kv.second.d_ops); cudaFree(kv.second.tagged); }
     g.nets.clear();
 }
 
@@ -639,7 +642,7 @@ static NetPlan& get_net_plan(Config* p, RunState* s, TransformerWeights* w) {
     memcpy(key.data() + sizeof(Config) + sizeof(RunState), w, sizeof(TransformerWeights));
     NetPlan& np = g.nets[(const void*)s];
     if (np.key == key) return np;
-    if (np.d_ops) { LQ4_CHECK(cudaStreamSynchronize(g.stream)); cudaFree(np.d_ops); cudaFree(np.kraw); np.d_ops = nullptr; np.kraw = nullptr; }
+    if (np.d_ops) { LQ4_CHECK(cudaStreamSynchronize(g.stream)); cudaFree(np.d_ops); cudaFree(np.tagged); np.d_ops = nullptr; np.tagged = nullptr; }
     np.key = key;
     np.ok = false;
 
@@ -648,7 +651,17 @@ static NetPlan& get_net_plan(Config* p, RunState* s, TransformerWeights* w) {
     const int kv_dim = (p->dim * p->n_kv_heads) / p->n_heads;
     const int kv_mul = p->n_heads / p->n_kv_heads;
     if ((head_size != 32 && head_size != 64 && head_size != 128) || p->seq_len > MAX_SEQ_LEN_SMEM_KERNEL) return np;
-    LQ4_CHECK(cudaMalloc((void**)&np.kraw, sizeof(half) * kv_dim));
+    // activations of the fused step travel as tagged 32-bit words (interp_sm100.cuh, "flag-in-data"): no grid barrier
+    // between the op that writes a vector and the op that reads it
+    const size_t ntag = (size_t)3 * dim + hidden + 2 * kv_dim;
+    LQ4_CHECK(cudaMalloc((void**)&np.tagged, ntag * sizeof(uint32_t)));
+    LQ4_CHECK(cudaMemset(np.tagged, 0, ntag * sizeof(uint32_t)));
+    uint32_t* xt = np.tagged;
+    uint32_t* xbt = xt + dim;
+    uint32_t* hbt = xbt + dim;
+    uint32_t* qt = hbt + hidden;
+    uint32_t* krawt = qt + dim;
+    uint32_t* vrawt = krawt + kv_dim;
     const float2* rope_tab = rope_table(p->rope_theta, head_size, p->seq_len);
 
     std::vector<Op> ops;
@@ -656,54 +669,54 @@ static NetPlan& get_net_plan(Config* p, RunState* s, TransformerWeights* w) {
     for (int l = 0; l < p->n_layers && ok; l++) {
         PerLayerWeight& L = w->layers[l];
         const int loff = l * p->seq_len * kv_dim;
-        {
+        {   // RMSNorm + q | k | v  (first layer: + embedding gather)
             Op op; memset(&op, 0, sizeof op);
             op.kind = OP_GEMV;
             op.x = s->x; op.norm_w = L.rms_att_weight;
-            if (l == 0) { op.emb = w->token_embedding_table; op.tokens = s->shared_data->tokens; op.x_copy = s->x; }
-            op.sync_before = (l > 0);
-            set_seg(op.seg[0], &L.wq_q, s->q, dim, 0, 0);
-            set_seg(op.seg[1], &L.wq_k, np.kraw, kv_dim, 0, 0);                     // rotated into the cache by OP_ATTN
-            set_seg(op.seg[2], &L.wq_v, s->value_cache, kv_dim, loff, kv_dim);
+            if (l == 0) { op.emb = w->token_embedding_table; op.tokens = s->shared_data->tokens; }
+            else op.xt = xt;
+            set_seg(op.seg[0], &L.wq_q, nullptr, dim, 0, 0, qt);
+            set_seg(op.seg[1], &L.wq_k, nullptr, kv_dim, 0, 0, krawt);               // rotated into the cache by OP_ATTN
+            set_seg(op.seg[2], &L.wq_v, s->value_cache, kv_dim, loff, kv_dim, vrawt);
             const int nc[3] = {dim, kv_dim, kv_dim};
             ok = ok && q4_op_shape(op, dim, nc, 3, false);
             ops.push_back(op);
         }
-        {
+        {   // RoPE + attention
             Op op; memset(&op, 0, sizeof op);
-            fill_attn_op(op, s->xb, s->q, s->key_cache + loff, s->value_cache + loff, nullptr, p->n_heads, head_size, kv_mul,
+            fill_attn_op(op, nullptr, s->q, s->key_cache + loff, s->value_cache + loff, nullptr, p->n_heads, head_size, kv_mul,
                          p->seq_len);
-            op.kraw = np.kraw; op.rope_tab = rope_tab;
-            op.sync_before = 1;
+            op.qt = qt; op.krawt = krawt; op.vrawt = vrawt; op.attn_out32 = xbt; op.rope_tab = rope_tab;
             ops.push_back(op);
         }
-        {
+        {   // o + residual
             Op op; memset(&op, 0, sizeof op);
-            op.kind = OP_GEMV; op.x = s->xb; op.accum = 1; op.sync_before = 1;
-            set_seg(op.seg[0], &L.wq_o, s->x, dim, 0, 0);
+            op.kind = OP_GEMV; op.x = s->xb; op.xt = xbt; op.accum = 1;
+            if (l == 0) { op.res_emb = w->token_embedding_table; op.tokens = s->shared_data->tokens; }
+            set_seg(op.seg[0], &L.wq_o, nullptr, dim, 0, 0, xt);
             ok = ok && q4_op_shape(op, dim, &dim, 1, false);
             ops.push_back(op);
         }
-        {
+        {   // RMSNorm + gate/up + SiLU
             Op op; memset(&op, 0, sizeof op);
-            op.kind = OP_FFN; op.x = s->x; op.norm_w = L.rms_ffn_weight; op.sync_before = 1;
-            set_seg(op.seg[0], &L.wq_gate, s->hb, hidden, 0, 0);
-            set_seg(op.seg[1], &L.wq_up, s->hb, hidden, 0, 0);
+            op.kind = OP_FFN; op.x = s->x; op.xt = xt; op.norm_w = L.rms_ffn_weight;
+            set_seg(op.seg[0], &L.wq_gate, nullptr, hidden, 0, 0, hbt);
+            set_seg(op.seg[1], &L.wq_up, nullptr, hidden, 0, 0, hbt);
             const int nc[2] = {hidden, hidden};
             ok = ok && q4_op_shape(op, dim, nc, 2, true);
             ops.push_back(op);
         }
-        {
+        {   // down + residual
             Op op; memset(&op, 0, sizeof op);
-            op.kind = OP_GEMV; op.x = s->hb; op.accum = 1; op.sync_before = 1;
-            set_seg(op.seg[0], &L.wq_down, s->x, dim, 0, 0);
+            op.kind = OP_GEMV; op.x = s->hb; op.xt = hbt; op.accum = 1;
+            set_seg(op.seg[0], &L.wq_down, nullptr, dim, 0, 0, xt);
             ok = ok && q4_op_shape(op, hidden, &dim, 1, false);
             ops.push_back(op);
         }
     }
-    {
+    {   // final RMSNorm + classifier; the logits stay plain fp16 (the API exposes them), so the sampler keeps its barrier
         Op op; memset(&op, 0, sizeof op);
-        op.kind = OP_CLS; op.x = s->x; op.norm_w = w->rms_final_weight; op.sync_before = 1;
+        op.kind = OP_CLS; op.x = s->x; op.xt = xt; op.norm_w = w->rms_final_weight;
         op.seg[0].w = reinterpret_cast<const uint32_t*>(w->wcls);
         op.seg[0].out = s->logits;
         op.alpha = 1.0f;
@@ -967,7 +980,7 @@ void lq4_free_transformer(Transformer* t) {
     RunState* s = &t->state;
     cudaStreamSynchronize(g.stream);
     auto np = g.nets.find((const void*)s);
-    if (np != g.nets.end()) { cudaFree(np->second.d_ops); cudaFree(np->second.kraw); g.nets.erase(np); }
+    if (np != g.nets.end()) { cudaFree(np->second.d_ops); cudaFree(np->second.tagged); g.nets.erase(np); }
     cudaFree(s->x); cudaFree(s->xb); cudaFree(s->pos); cudaFree(s->hb); cudaFree(s->q); cudaFree(s->att);
     cudaFree(s->logits); cudaFree(s->key_cache); cudaFree(s->value_cache); cudaFreeHost(s->shared_data);
     if (s->logits_array) cudaFree(s->logits_array);

@@ -48,7 +48,8 @@ struct Seg {
     const uint32_t* w;     // [ncols][K/8] packed nibbles   (OP_CLS: fp16 weights [rows][row_stride])
     const uint32_t* z;     // [ncols][zh]
     const uint16_t* s;     // [ncols][G]
-    half* out;             // output vector of this matrix
+    half* out;             // output vector of this matrix (fp16), or nullptr when only the tagged copy is wanted
+    uint32_t* out32;       // tagged output vector (see "flag-in-data" below) or nullptr
     int ncols;
     int loff;              // element offset added to out together with pos*pos_stride (KV-cache row), see pos_stride
     int pos_stride;        // 0: out is used as is; else out += loff + pos * pos_stride  (gpu_kernels.h:224-226)
@@ -69,11 +70,13 @@ struct Op {
     int sync_before;       // grid barrier before the consumers read this op's inputs
     Seg seg[3];
     // activation input
+    const uint32_t* xt;    // [K] tagged activations written earlier in this launch by other CTAs, or nullptr: use x
     const half* x;         // [K]
     const half* norm_w;    // fused RMSNorm weight (gpu_kernels.h:72-105) or nullptr
     const half* emb;       // x = emb[tokens[pos]] (copy_embedding_kernel, :61-69) when non-null
     const int* tokens;
-    half* x_copy;          // CTA 0 stores the gathered embedding row here (the residual stream)
+    half* x_copy;          // CTA 0 stores the gathered embedding row here (the residual stream); op-by-op path only
+    const half* res_emb;   // accumulating GEMV: the residual is this embedding table's row tokens[pos] instead of the old output
     // OP_CLS
     int row_stride;        // elements between rows
     float alpha;
@@ -84,6 +87,10 @@ struct Op {
     const half* vcache;
     half* att_out;         // optional probabilities [n_heads][pos+1]
     half* attn_out;        // [n_heads*head_size]
+    const uint32_t* qt;    // tagged q | un-rotated k row | v row of this step (fused path) or nullptr: q / kraw / the cache row
+    const uint32_t* krawt;
+    const uint32_t* vrawt;
+    uint32_t* attn_out32;  // tagged output or nullptr
     const float2* rope_tab;
     int n_heads, head_size, kv_mul, kv_stride, max_seq;
     float att_alpha;
@@ -107,6 +114,7 @@ struct InterpParams {
     int meta_bytes;        // one scale/zero buffer (there are two)
     int xs_bytes;          // activation staging area (aliased with the attention scratch)
     int write_token;       // overrides Op::write_token of OP_ARGMAX when >= 0
+    unsigned seq_base;     // launch counter * nops: makes the activation tags of this launch unique
     unsigned* sync;        // [2] grid barrier counter, exit counter (zero between launches)
     const int* pPos;       // device position
     unsigned long long* trace;   // optional [nops + 1] timestamps (ns): CTA 0 at the start of each op, and at the end
@@ -183,6 +191,53 @@ __device__ __forceinline__ uint32_t ld_cg_u16(const void* p) {
     asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(r) : "l"(p));
     return (uint32_t)r;
 }
+// ------------------------------------------------------------------------------------------------
+// Flag-in-data activations.  Inside one launch an activation vector is written by many CTAs and read by all of
+// them.  Instead of a grid barrier between writer and readers, every element travels as one 32-bit word
+// (tag << 16 | fp16 bits), the tag naming the op that wrote it in this launch; a reader simply re-reads a word
+// until its tag is the expected one.  A 32-bit store is indivisible, so no ordering between words is needed.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_tagged(uint32_t* p, uint32_t tag, uint32_t hbits) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"((tag << 16) | (hbits & 0xFFFFu)) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_tagged_any(const uint32_t* p) {      // current word, whatever its tag (residual read by its only writer)
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t poll1(const uint32_t* p, uint32_t tag) {   // fp16 bits of one element
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    if ((v >> 16) != tag) {
+        const unsigned long long t0 = global_ns();
+        do {
+            asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+            if ((v >> 16) != tag && global_ns() - t0 > kWaitLimitNs) asm volatile("trap;");
+        } while ((v >> 16) != tag);
+    }
+    return v & 0xFFFFu;
+}
+__device__ __forceinline__ bool tags_ok(const uint4& v, uint32_t tag) {
+    return ((v.x >> 16) == tag) & ((v.y >> 16) == tag) & ((v.z >> 16) == tag) & ((v.w >> 16) == tag);
+}
+__device__ __forceinline__ uint4 ld_vol_v4(const uint32_t* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+// eight consecutive elements as four words of packed fp16 pairs (the layout an 8-half vector load returns)
+__device__ __forceinline__ uint4 poll8(const uint32_t* p, uint32_t tag) {
+    uint4 a = ld_vol_v4(p), b = ld_vol_v4(p + 4);
+    if (!(tags_ok(a, tag) && tags_ok(b, tag))) {
+        const unsigned long long t0 = global_ns();
+        do {
+            a = ld_vol_v4(p); b = ld_vol_v4(p + 4);
+            if (global_ns() - t0 > kWaitLimitNs) asm volatile("trap;");
+        } while (!(tags_ok(a, tag) && tags_ok(b, tag)));
+    }
+    return make_uint4((a.x & 0xFFFFu) | (a.y << 16), (a.z & 0xFFFFu) | (a.w << 16), (b.x & 0xFFFFu) | (b.y << 16), (b.z & 0xFFFFu) | (b.w << 16));
+}
+
 __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
     uint4 r;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
@@ -402,6 +457,7 @@ struct Ctx {
     unsigned mcount;          // INT4 ops so far (scale/zero buffer = mcount & 1)
     int meta_pending;         // scale/zero buffer to hand back to the producer once every warp has left the op, or -1
     unsigned nsync;           // grid barriers taken so far
+    uint32_t tag_in, tag_out; // activation tags: of the op whose output this op reads, and of this op
     unsigned long long* tr;   // detailed phase trace of the current op (this CTA's 8 entries) or nullptr
 };
 __device__ __forceinline__ void cyc_mark(const Ctx& c, int k) {      // SM clock, warp 0 lane 0: sub-microsecond phases
@@ -477,7 +533,7 @@ __device__ float stage_raw_and_scale(Ctx& c, const Op& op, const half* xin, uint
     int r = 0;
 #pragma unroll 1
     for (int u = c.ctid; u * 8 < K; u += c.nthreads, r++) {
-        const uint4 xv = ld_cg_v4(xin + u * 8);
+        const uint4 xv = (op.xt != nullptr) ? poll8(op.xt + u * 8, c.tag_in) : ld_cg_v4(xin + u * 8);
         uint4 wv;
         if (r == 0) wv = nr.w[0]; else if (r == 1) wv = nr.w[1]; else if (r == 2) wv = nr.w[2]; else wv = ldg_stream_v4(op.norm_w + u * 8);
         sts_v4_u32(xraw + u * 16, xv);
@@ -529,6 +585,8 @@ __device__ void stage_x_pairs(Ctx& c, const Op& op, const NormRegs& nr) {
                 if (norm) {
                     r0[v] = lds_v4(xraw + k0 * 2); r1[v] = lds_v4(xraw + k1 * 2);
                     n0[v] = lds_v4(xraw + K * 2 + k0 * 2); n1[v] = lds_v4(xraw + K * 2 + k1 * 2);
+                } else if (op.xt != nullptr) {
+                    r0[v] = poll8(op.xt + k0, c.tag_in); r1[v] = poll8(op.xt + k1, c.tag_in);
                 } else {
                     r0[v] = ld_cg_v4(xin + k0); r1[v] = ld_cg_v4(xin + k1);
                 }
@@ -724,18 +782,30 @@ __device__ void run_q4(Ctx& c, const Op& op, const NormRegs& nr) {
                 float val = v0;
                 val = __fmul_rn(val, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-val))));
                 val = __fmul_rn(val, v1);
-                op.seg[0].out[col] = __float2half_rn(val);
+                const uint32_t hb = f2h_bits(val);
+                if (op.seg[0].out32 != nullptr) st_tagged(op.seg[0].out32 + col, c.tag_out, hb);
+                else op.seg[0].out[col] = __ushort_as_half((unsigned short)hb);
             } else {
                 const Seg& sg = op.seg[seg];
                 half* dst = sg.out;
-                if (sg.pos_stride != 0) dst += sg.loff + (size_t)c.pos * sg.pos_stride;
+                if (dst != nullptr && sg.pos_stride != 0) dst += sg.loff + (size_t)c.pos * sg.pos_stride;
                 float s0 = v0, s1 = v1;
                 if (op.accum) {
-                    s0 = s0 + h2f_bits(ld_cg_u16(dst + col));
-                    s1 = s1 + h2f_bits(ld_cg_u16(dst + col + 1));
+                    uint32_t o0, o1;
+                    if (op.res_emb != nullptr) {                 // first layer: the residual is the embedding row itself
+                        const half* e = op.res_emb + (size_t)op.tokens[c.pos] * sg.ncols + col;
+                        o0 = ldg_stream_u16(e); o1 = ldg_stream_u16(e + 1);
+                    } else if (sg.out32 != nullptr) {
+                        o0 = ld_tagged_any(sg.out32 + col) & 0xFFFFu; o1 = ld_tagged_any(sg.out32 + col + 1) & 0xFFFFu;
+                    } else {
+                        o0 = ld_cg_u16(dst + col); o1 = ld_cg_u16(dst + col + 1);
+                    }
+                    s0 = s0 + h2f_bits(o0);
+                    s1 = s1 + h2f_bits(o1);
                 }
-                dst[col] = __float2half_rn(s0);
-                dst[col + 1] = __float2half_rn(s1);
+                const uint32_t h0 = f2h_bits(s0), h1 = f2h_bits(s1);
+                if (sg.out32 != nullptr) { st_tagged(sg.out32 + col, c.tag_out, h0); st_tagged(sg.out32 + col + 1, c.tag_out, h1); }
+                if (dst != nullptr) { dst[col] = __ushort_as_half((unsigned short)h0); dst[col + 1] = __ushort_as_half((unsigned short)h1); }
             }
         }
     }
@@ -772,7 +842,7 @@ __device__ void run_cls(Ctx& c, const Op& op, const NormRegs& nr) {
                     xw[q] = lo | (hi << 16);
                 }
             } else {
-                xv = ld_cg_v4(op.x + u * 8);
+                xv = (op.xt != nullptr) ? poll8(op.xt + u * 8, c.tag_in) : ld_cg_v4(op.x + u * 8);
             }
             sts_v4_u32(c.sm.xs + u * 16, xv);
         }
@@ -898,11 +968,17 @@ __device__ void run_attn_t(Ctx& c, const Op& op, bool prefetched) {
                 const float2 cs = op.rope_tab[(size_t)pos * (hs / 2) + i];
                 half* q = op.q + (size_t)h * hs;
                 const half* kr = op.kraw + (size_t)kvh * hs;
-                const uint32_t q0b = ld_cg_u16(q + i), q1b = ld_cg_u16(q + i + hs / 2), k0b = ld_cg_u16(kr + i), k1b = ld_cg_u16(kr + i + hs / 2);
+                uint32_t q0b, q1b, k0b, k1b;
+                if (op.qt != nullptr) {      // fused path: q and the un-rotated k row arrive as tagged words from the q|k|v op
+                    q0b = poll1(op.qt + (size_t)h * hs + i, c.tag_in); q1b = poll1(op.qt + (size_t)h * hs + i + hs / 2, c.tag_in);
+                    k0b = poll1(op.krawt + (size_t)kvh * hs + i, c.tag_in); k1b = poll1(op.krawt + (size_t)kvh * hs + i + hs / 2, c.tag_in);
+                } else {
+                    q0b = ld_cg_u16(q + i); q1b = ld_cg_u16(q + i + hs / 2); k0b = ld_cg_u16(kr + i); k1b = ld_cg_u16(kr + i + hs / 2);
+                }
                 const float q0 = h2f_bits(q0b), q1 = h2f_bits(q1b), k0 = h2f_bits(k0b), k1 = h2f_bits(k1b);
                 const half o0 = __float2half_rn(__fmaf_rn(q0, cs.x, -__fmul_rn(q1, cs.y)));
                 const half o1 = __float2half_rn(__fmaf_rn(q1, cs.x, __fmul_rn(q0, cs.y)));
-                q[i] = o0; q[i + hs / 2] = o1;
+                if (op.qt == nullptr) { q[i] = o0; q[i + hs / 2] = o1; }     // the reference rotates q in place; nobody reads it in the fused path
                 qs[i] = __half2float(o0); qs[i + hs / 2] = __half2float(o1);
                 const half r0 = __float2half_rn(__fmaf_rn(k0, cs.x, -__fmul_rn(k1, cs.y)));
                 const half r1 = __float2half_rn(__fmaf_rn(k0, cs.y, __fmul_rn(k1, cs.x)));
@@ -912,7 +988,8 @@ __device__ void run_attn_t(Ctx& c, const Op& op, bool prefetched) {
                     kd[i] = r0; kd[i + hs / 2] = r1;
                 }
             }
-            for (int i = tid - 64; i >= 0 && i < hs; i += nt) vrow[i] = h2f_bits(ld_cg_u16(vbase + (size_t)pos * op.kv_stride + i));
+            for (int i = tid - 64; i >= 0 && i < hs; i += nt)
+                vrow[i] = h2f_bits(op.vrawt != nullptr ? poll1(op.vrawt + (size_t)kvh * hs + i, c.tag_in) : ld_cg_u16(vbase + (size_t)pos * op.kv_stride + i));
         } else {
             for (int i = tid; i < hs; i += nt) {
                 qs[i] = h2f_bits(ld_cg_u16(op.q + (size_t)h * hs + i));
@@ -920,7 +997,9 @@ __device__ void run_attn_t(Ctx& c, const Op& op, bool prefetched) {
                 vrow[i] = h2f_bits(ld_cg_u16(vbase + (size_t)pos * op.kv_stride + i));
             }
         }
-        if (tid < 64 && nt <= 64) for (int i = tid; i < hs; i += nt) vrow[i] = h2f_bits(ld_cg_u16(vbase + (size_t)pos * op.kv_stride + i));
+        if (tid < 64 && nt <= 64)
+            for (int i = tid; i < hs; i += nt)
+                vrow[i] = h2f_bits(op.vrawt != nullptr ? poll1(op.vrawt + (size_t)kvh * hs + i, c.tag_in) : ld_cg_u16(vbase + (size_t)pos * op.kv_stride + i));
         // ---- scores (lane chain over j = 32 i + lane, gpu_kernels.h:154-159), K tile by tile ----
 #pragma unroll 1
         for (int tile0 = 0; tile0 < pos; tile0 += kAttnTile) {
@@ -1039,7 +1118,8 @@ __device__ void run_attn_t(Ctx& c, const Op& op, bool prefetched) {
             for (int o = 1; o < 32; o <<= 1)
 #pragma unroll
                 for (int w = 0; w < 32; w += 2 * o) v[w] = v[w] + v[w + o];
-            op.attn_out[(size_t)h * hs + i] = __float2half_rn(v[0]);
+            if (op.attn_out32 != nullptr) st_tagged(op.attn_out32 + (size_t)h * hs + i, c.tag_out, f2h_bits(v[0]));
+            else op.attn_out[(size_t)h * hs + i] = __float2half_rn(v[0]);
         }
         named_bar(kBarAll, nt);
         trace_mark(c, 7);
@@ -1147,7 +1227,7 @@ __global__ void __launch_bounds__(32 * (kMaxConsumerWarps + 1), 1) interp_kernel
     c.scratch = smem + kCtrlBytes;
     c.nwc = P.nwc; c.nthreads = P.nwc * 32; c.warp = warp; c.lane = lane; c.ctid = threadIdx.x;
     c.pos = (P.pPos != nullptr) ? *P.pPos : 0;
-    c.qbase = 0; c.mcount = 0; c.meta_pending = -1; c.nsync = 0; c.tr = nullptr;
+    c.qbase = 0; c.mcount = 0; c.meta_pending = -1; c.nsync = 0; c.tr = nullptr; c.tag_in = c.tag_out = 0;
 
     const Op& op = *reinterpret_cast<const Op*>(smem + kOpOffset);
     for (int o = 0; o < P.nops; o++) {
@@ -1165,6 +1245,8 @@ __global__ void __launch_bounds__(32 * (kMaxConsumerWarps + 1), 1) interp_kernel
             if (sync_before) grid_arrive(P.sync);
         }
         c.meta_pending = -1;
+        c.tag_out = ((P.seq_base + (unsigned)o + 1u) & 0x7FFFu) | 0x8000u;     // never 0: a zeroed buffer is never "fresh"
+        c.tag_in = ((P.seq_base + (unsigned)o) & 0x7FFFu) | 0x8000u;           // the previous op's
         NormRegs nr;
         load_norm_regs(c, ops[o], nr);             // in flight while the grid barrier completes
         const bool attn_pref = (ops[o].kind == OP_ATTN) && sync_before;
