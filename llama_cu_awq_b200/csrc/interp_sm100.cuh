@@ -231,6 +231,7 @@ __device__ __forceinline__ uint4 poll8(const uint32_t* p, uint32_t tag) {
     if (!(tags_ok(a, tag) && tags_ok(b, tag))) {
         const unsigned long long t0 = global_ns();
         do {
+            __nanosleep(40);        // idle CTAs poll for a long time (e.g. the 116 without a head during attention): stay off the L2
             a = ld_vol_v4(p); b = ld_vol_v4(p + 4);
             if (global_ns() - t0 > kWaitLimitNs) asm volatile("trap;");
         } while (!(tags_ok(a, tag) && tags_ok(b, tag)));
@@ -970,8 +971,16 @@ __device__ void run_attn_t(Ctx& c, const Op& op, bool prefetched) {
                 const half* kr = op.kraw + (size_t)kvh * hs;
                 uint32_t q0b, q1b, k0b, k1b;
                 if (op.qt != nullptr) {      // fused path: q and the un-rotated k row arrive as tagged words from the q|k|v op
-                    q0b = poll1(op.qt + (size_t)h * hs + i, c.tag_in); q1b = poll1(op.qt + (size_t)h * hs + i + hs / 2, c.tag_in);
-                    k0b = poll1(op.krawt + (size_t)kvh * hs + i, c.tag_in); k1b = poll1(op.krawt + (size_t)kvh * hs + i + hs / 2, c.tag_in);
+                    const uint32_t* pq = op.qt + (size_t)h * hs + i;
+                    const uint32_t* pk = op.krawt + (size_t)kvh * hs + i;
+                    const uint32_t tag = c.tag_in;
+                    const unsigned long long t0 = global_ns();
+                    for (;;) {               // the four words are fetched together: one round trip per attempt, not four
+                        q0b = ld_tagged_any(pq); q1b = ld_tagged_any(pq + hs / 2); k0b = ld_tagged_any(pk); k1b = ld_tagged_any(pk + hs / 2);
+                        if (((q0b >> 16) == tag) & ((q1b >> 16) == tag) & ((k0b >> 16) == tag) & ((k1b >> 16) == tag)) break;
+                        if (global_ns() - t0 > kWaitLimitNs) asm volatile("trap;");
+                    }
+                    q0b &= 0xFFFFu; q1b &= 0xFFFFu; k0b &= 0xFFFFu; k1b &= 0xFFFFu;
                 } else {
                     q0b = ld_cg_u16(q + i); q1b = ld_cg_u16(q + i + hs / 2); k0b = ld_cg_u16(kr + i); k1b = ld_cg_u16(kr + i + hs / 2);
                 }
