@@ -141,6 +141,22 @@ def cpu_baseline_sample(path, cfg, threads):
             "sample": f"1 token at pos 0: {nl} of {cfg['n_layers']} layers ({t_layers:.2f}s) scaled to full depth + classifier ({t_cls:.2f}s), oracle/cpu_ref.c"}
 
 
+def max_over_ranks(value, world, device="cuda"):
+    """Replicas: the job's time is the slowest rank's (max over ranks); a plain float in, a plain float out."""
+    if world <= 1:
+        return float(value)
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(value)], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def aggregate_throughput(units_per_rank, seconds, world, device="cuda"):
+    """Whole-job throughput of `world` independent replicas: all units / the slowest rank's time."""
+    return world * units_per_rank / max_over_ranks(seconds, world, device)
+
+
 def run_reference_arm(args):
     import llama_cu_awq_b200 as E
     lib = E.lib()
@@ -254,10 +270,7 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     clk = clocks.stop()
-    if world > 1:
-        tms = torch.tensor([ms], device="cuda")
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
+    ms = max_over_ranks(ms, world)
     tokens_dev = [int(t.state.shared_data.contents.tokens[i]) for i in range(K + 1)]
 
     # ---- e2e: the host-buffer API, wall clock inside the call (host wait + pinned hand-off per token) ----
@@ -268,9 +281,7 @@ def main():
     e2e_val = (n - 1) / secs.value if secs.value > 0 else None
     assert list(out)[1:n] == tokens_dev[1:n], "pipelined host API and raw enqueue disagree on token ids"
     if world > 1:
-        te = torch.tensor([secs.value], device="cuda")
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_val = (n - 1) / float(te.item())
+        e2e_val = (n - 1) / max_over_ranks(secs.value, world)
 
     # ---- roofline ----
     # The decode step is ONE launch of the persistent kernel (interp_kernel), so the dominant kernel's launch
@@ -311,7 +322,7 @@ def main():
     ach = ffn_bytes / (ffn_us * 1e-6) / 1e9
     roofline_ffn = {"bound": "hbm", "kernel": "interp_kernel, single op lq4_ffn_matvec_silu (K=%d N=%d), launch overhead included" % (d, h),
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "bytes_per_launch": ffn_bytes, "us_per_launch": ffn_us}
-    value = world * K / (ms * 1e-3)
+    value = aggregate_throughput(K, ms * 1e-3, 1) * world      # ms is already the max over ranks
 
     line = {"metric": "decode tokens/sec (seq_len=1)", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
