@@ -149,6 +149,13 @@ void lq4_enqueue_step(Transformer* t, Sampler* sampler, int seq_len, int gen_tok
 int lq4_step(Transformer* t, Sampler* sampler, int gen_token, lq4_half* logits_out, int* next_token_out);
 void lq4_reset(Transformer* t, const int* tokens, int n);   /* generate() init, llama2_q4.cu:461-463 */
 
+/* ---- tensor parallel, one process per GPU (new: the reference is single-GPU).  Column slices of every matrix per rank;
+ * activations are broadcast by peer stores over NVLink (no collective call, no cross-GPU barrier); ids are bit-identical
+ * to one GPU.  Order: lq4_tp_config -> lq4_build_transformer -> exchange lq4_tp_export handles -> lq4_tp_import each. ---- */
+int lq4_tp_config(int rank, int world);
+int lq4_tp_export(Transformer* t, void* handle64);
+int lq4_tp_import(Transformer* t, int peer, const void* handle64);
+
 /* ---- seeded random-init files in the reference formats (no network for real checkpoints) ---- */
 size_t lq4_write_synth_model(const char* path, const Config* cfg, unsigned long long seed);
 size_t lq4_write_synth_tokenizer(const char* path, int vocab_size);

@@ -97,6 +97,9 @@ _SIGNATURES = {
     "lq4_enqueue_step": (None, [C.POINTER(Transformer), C.POINTER(Sampler), C.c_int, C.c_int]),
     "lq4_step": (C.c_int, [C.POINTER(Transformer), C.POINTER(Sampler), C.c_int, _P, C.POINTER(C.c_int)]),
     "lq4_reset": (None, [C.POINTER(Transformer), C.POINTER(C.c_int), C.c_int]),
+    "lq4_tp_config": (C.c_int, [C.c_int, C.c_int]),
+    "lq4_tp_export": (C.c_int, [C.POINTER(Transformer), _P]),
+    "lq4_tp_import": (C.c_int, [C.POINTER(Transformer), C.c_int, _P]),
     "lq4_write_synth_model": (C.c_size_t, [C.c_char_p, C.POINTER(Config), C.c_ulonglong]),
     "lq4_write_synth_tokenizer": (C.c_size_t, [C.c_char_p, C.c_int]),
 }
@@ -167,3 +170,15 @@ def kv_bytes_at(cfg: dict, pos: int) -> int:
     """KV-cache bytes read+written at position pos: (pos+1) rows of K and V read, one row of each written."""
     kv = cfg["dim"] * cfg["n_kv_heads"] // cfg["n_heads"]
     return (pos + 1) * 2 * kv * 2 * cfg["n_layers"] + 2 * kv * 2 * cfg["n_layers"]
+
+
+def tp_connect(lib, transformer, rank: int, world: int) -> None:
+    """Exchange the CUDA IPC handles of the ranks' activation buffers over torch.distributed (plumbing only) and map them."""
+    import torch.distributed as dist
+    buf = C.create_string_buffer(64)
+    assert lib.lq4_tp_export(C.byref(transformer), buf) == 0, lib.lq4_last_error()
+    handles = [None] * world
+    dist.all_gather_object(handles, bytes(buf.raw))
+    for peer in range(world):
+        assert lib.lq4_tp_import(C.byref(transformer), peer, C.create_string_buffer(handles[peer], 64)) == 0, lib.lq4_last_error()
+    dist.barrier()

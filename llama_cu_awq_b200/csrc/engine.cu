@@ -49,8 +49,9 @@ struct NetPlan {
     Plan plan;
     Op* d_ops = nullptr;
     int nops = 0;              // including the trailing OP_ARGMAX
-    uint32_t* tagged = nullptr;   // flag-in-data activation vectors of the fused step: x | xb | hb | q | k (un-rotated) | v
-    int opt_tagged = 1;
+    uint32_t* tagged = nullptr;   // flag-in-data activation vectors of the fused step: x | xb | hb | q | k (un-rotated) | v | argmax candidates
+    uint32_t* peers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // every rank's `tagged`, mapped here
+    int world = 1, rank = 0;
     std::vector<char> key;     // Config + pointers the table was built from
     bool ok = false;           // false: some shape is not supported by the persistent kernel
 };
@@ -71,6 +72,7 @@ struct Engine {
     std::map<const void*, NetPlan> nets;
     unsigned* sync = nullptr;
     unsigned long long launch_seq = 1;   // persistent-kernel launches so far (activation tags)
+    int tp_rank = 0, tp_world = 1;       // tensor parallel: one process per GPU, this one's rank
     int opt_trace = 0;      // record per-op timestamps of fused steps (development aid)
     int opt_trace_op = -1;  // op whose phases are recorded per CTA
     unsigned long long* trace = nullptr;
@@ -283,13 +285,21 @@ int op_meta_bytes(const Op& op, int grid) {
     return cols * (q4_groups(op.K) * 2 + q4_zh(op.K) * 4) + 64;
 }
 
-void set_seg(Seg& sg, const QWeight* w, half* out, int ncols, int loff, int pos_stride, uint32_t* out32 = nullptr) {
+void set_seg(Seg& sg, const QWeight* w, half* out, int ncols, int loff, int pos_stride, uint32_t* out32 = nullptr, int bcast = 0) {
     sg.w = w->weight; sg.z = w->zeros; sg.s = reinterpret_cast<const uint16_t*>(w->scales);
-    sg.out = out; sg.out32 = out32; sg.ncols = ncols; sg.loff = loff; sg.pos_stride = pos_stride; sg.pad_ = 0;
+    sg.out = out; sg.out32 = out32; sg.ncols = ncols; sg.loff = loff; sg.pos_stride = pos_stride; sg.bcast = bcast;
+}
+// columns [c0, c0 + n) of a QWeight(K, N): a contiguous byte range of each of its three arrays (tensor-parallel slices)
+QWeight slice_cols(const QWeight& w, int K, int c0) {
+    QWeight r;
+    r.weight = w.weight + (size_t)c0 * (size_t)(divUp(K, 32) * 4);
+    r.zeros = w.zeros + (size_t)c0 * (size_t)q4_zh(K);
+    r.scales = w.scales + (size_t)c0 * (size_t)q4_groups(K);
+    return r;
 }
 
 void launch_interp(const Plan& pl, const Op* d_ops, int nops, const Op* one, const int* pPos, int write_token,
-                   bool cooperative, int grid) {
+                   bool cooperative, int grid, const NetPlan* tp = nullptr) {
     InterpParams P;
     memset(&P, 0, sizeof P);
     P.ops = d_ops; P.nops = nops;
@@ -297,6 +307,14 @@ void launch_interp(const Plan& pl, const Op* d_ops, int nops, const Op* one, con
     P.write_token = write_token;
     P.sync = g.sync; P.pPos = pPos;
     P.seq_base = (unsigned)((g.launch_seq++ * (unsigned long long)std::max(nops, 1)) & 0x3FFFFFFFull);
+    P.rank = 0; P.world = 1;
+    if (tp != nullptr) {
+        P.rank = tp->rank; P.world = tp->world;
+        for (int r = 0; r < tp->world; r++) {
+            if (tp->peers[r] == nullptr) { fprintf(stderr, "lq4: tensor-parallel peer %d has not been imported (lq4_tp_import)\n", r); exit(EXIT_FAILURE); }
+            P.peers[r] = tp->peers[r];
+        }
+    }
     if (g.opt_trace && d_ops != nullptr && nops + 1 <= 2048) {
         if (!g.trace) { LQ4_CHECK(cudaMalloc((void**)&g.trace, 8192 * sizeof(unsigned long long))); LQ4_CHECK(cudaMemset(g.trace, 0, 8192 * sizeof(unsigned long long))); }
         P.trace = g.trace;
@@ -636,7 +654,9 @@ static void run_network_unfused(int* pPos, Config* p, RunState* s, TransformerWe
 //   per layer  [embed+]RMSNorm+q|k|v  ->  RoPE+attention  ->  o+residual  ->  RMSNorm+gate/up+SiLU  ->  down+residual
 //   then       RMSNorm+classifier  ->  argmax
 static NetPlan& get_net_plan(Config* p, RunState* s, TransformerWeights* w) {
-    std::vector<char> key(sizeof(Config) + sizeof(RunState) + sizeof(TransformerWeights));
+    std::vector<char> key(sizeof(Config) + sizeof(RunState) + sizeof(TransformerWeights) + 2 * sizeof(int));
+    memcpy(key.data() + sizeof(Config) + sizeof(RunState) + sizeof(TransformerWeights), &g.tp_rank, sizeof(int));
+    memcpy(key.data() + sizeof(Config) + sizeof(RunState) + sizeof(TransformerWeights) + sizeof(int), &g.tp_world, sizeof(int));
     memcpy(key.data(), p, sizeof(Config));
     memcpy(key.data() + sizeof(Config), s, sizeof(RunState));
     memcpy(key.data() + sizeof(Config) + sizeof(RunState), w, sizeof(TransformerWeights));
@@ -651,17 +671,31 @@ static NetPlan& get_net_plan(Config* p, RunState* s, TransformerWeights* w) {
     const int kv_dim = (p->dim * p->n_kv_heads) / p->n_heads;
     const int kv_mul = p->n_heads / p->n_kv_heads;
     if ((head_size != 32 && head_size != 64 && head_size != 128) || p->seq_len > MAX_SEQ_LEN_SMEM_KERNEL) return np;
+    // Tensor parallel (T ranks, one process per GPU): every matrix is split by output columns, rank r owning the r-th
+    // contiguous slice (heads r*H/T.. for q|k|v and attention, hidden and dim slices for the FFN and the projections, vocabulary
+    // rows for the classifier).  Each column is still computed entirely by one thread in the reference's order, so results are
+    // bit-identical to one GPU.  The slices are expressed by offsetting the pointers: the kernel sees smaller matrices.
+    const int T = g.tp_world, R = g.tp_rank;
+    np.world = T; np.rank = R;
+    if (T > 1 && (p->n_heads % T || p->n_kv_heads % T || (dim / T) % 8 || (hidden / T) % 8 || (kv_dim / T) % 8 || (p->vocab_size / T) % 8 ||
+                  p->vocab_size % T || p->vocab_size > 65535 || T > 8)) return np;
+    const int sdim = dim / T, shid = hidden / T, skv = kv_dim / T, sheads = p->n_heads / T, svoc = p->vocab_size / T;
+    const int bc = (T > 1) ? 1 : 0;
     // activations of the fused step travel as tagged 32-bit words (interp_sm100.cuh, "flag-in-data"): no grid barrier
-    // between the op that writes a vector and the op that reads it
-    const size_t ntag = (size_t)3 * dim + hidden + 2 * kv_dim;
+    // between the op that writes a vector and the op that reads it; under tensor parallelism the writer stores into every
+    // rank's copy and each rank polls its own
+    const size_t ntag = (size_t)3 * dim + hidden + 2 * kv_dim + 16;
     LQ4_CHECK(cudaMalloc((void**)&np.tagged, ntag * sizeof(uint32_t)));
     LQ4_CHECK(cudaMemset(np.tagged, 0, ntag * sizeof(uint32_t)));
+    for (int r = 0; r < 8; r++) np.peers[r] = nullptr;
+    np.peers[R] = np.tagged;
     uint32_t* xt = np.tagged;
     uint32_t* xbt = xt + dim;
     uint32_t* hbt = xbt + dim;
     uint32_t* qt = hbt + hidden;
     uint32_t* krawt = qt + dim;
     uint32_t* vrawt = krawt + kv_dim;
+    uint32_t* cand = vrawt + kv_dim;
     const float2* rope_tab = rope_table(p->rope_theta, head_size, p->seq_len);
 
     std::vector<Op> ops;
@@ -669,64 +703,70 @@ static NetPlan& get_net_plan(Config* p, RunState* s, TransformerWeights* w) {
     for (int l = 0; l < p->n_layers && ok; l++) {
         PerLayerWeight& L = w->layers[l];
         const int loff = l * p->seq_len * kv_dim;
-        {   // RMSNorm + q | k | v  (first layer: + embedding gather)
+        const QWeight wq = slice_cols(L.wq_q, dim, R * sdim), wk = slice_cols(L.wq_k, dim, R * skv), wv = slice_cols(L.wq_v, dim, R * skv);
+        const QWeight wo = slice_cols(L.wq_o, dim, R * sdim), wg = slice_cols(L.wq_gate, dim, R * shid), wu = slice_cols(L.wq_up, dim, R * shid);
+        const QWeight wd = slice_cols(L.wq_down, hidden, R * sdim);
+        {   // RMSNorm + q | k | v of this rank's heads (first layer: + embedding gather); consumed by this rank's attention only
             Op op; memset(&op, 0, sizeof op);
             op.kind = OP_GEMV;
             op.x = s->x; op.norm_w = L.rms_att_weight;
             if (l == 0) { op.emb = w->token_embedding_table; op.tokens = s->shared_data->tokens; }
             else op.xt = xt;
-            set_seg(op.seg[0], &L.wq_q, nullptr, dim, 0, 0, qt);
-            set_seg(op.seg[1], &L.wq_k, nullptr, kv_dim, 0, 0, krawt);               // rotated into the cache by OP_ATTN
-            set_seg(op.seg[2], &L.wq_v, s->value_cache, kv_dim, loff, kv_dim, vrawt);
-            const int nc[3] = {dim, kv_dim, kv_dim};
+            set_seg(op.seg[0], &wq, nullptr, sdim, 0, 0, qt + R * sdim);
+            set_seg(op.seg[1], &wk, nullptr, skv, 0, 0, krawt + R * skv);              // rotated into the cache by OP_ATTN
+            set_seg(op.seg[2], &wv, s->value_cache + R * skv, skv, loff, kv_dim, vrawt + R * skv);
+            const int nc[3] = {sdim, skv, skv};
             ok = ok && q4_op_shape(op, dim, nc, 3, false);
             ops.push_back(op);
         }
-        {   // RoPE + attention
+        {   // RoPE + attention over this rank's heads; the output slice goes to every rank
             Op op; memset(&op, 0, sizeof op);
-            fill_attn_op(op, nullptr, s->q, s->key_cache + loff, s->value_cache + loff, nullptr, p->n_heads, head_size, kv_mul,
+            fill_attn_op(op, nullptr, s->q, s->key_cache + loff + R * skv, s->value_cache + loff + R * skv, nullptr, sheads, head_size, kv_mul,
                          p->seq_len);
-            op.qt = qt; op.krawt = krawt; op.vrawt = vrawt; op.attn_out32 = xbt; op.rope_tab = rope_tab;
+            op.kv_stride = kv_dim;
+            op.qt = qt + R * sdim; op.krawt = krawt + R * skv; op.vrawt = vrawt + R * skv;
+            op.attn_out32 = xbt + R * sdim; op.attn_bcast = bc; op.rope_tab = rope_tab;
             ops.push_back(op);
         }
-        {   // o + residual
+        {   // o + residual: this rank's slice of x, broadcast
             Op op; memset(&op, 0, sizeof op);
             op.kind = OP_GEMV; op.x = s->xb; op.xt = xbt; op.accum = 1;
-            if (l == 0) { op.res_emb = w->token_embedding_table; op.tokens = s->shared_data->tokens; }
-            set_seg(op.seg[0], &L.wq_o, nullptr, dim, 0, 0, xt);
-            ok = ok && q4_op_shape(op, dim, &dim, 1, false);
+            if (l == 0) { op.res_emb = w->token_embedding_table + R * sdim; op.res_stride = dim; op.tokens = s->shared_data->tokens; }
+            set_seg(op.seg[0], &wo, nullptr, sdim, 0, 0, xt + R * sdim, bc);
+            ok = ok && q4_op_shape(op, dim, &sdim, 1, false);
             ops.push_back(op);
         }
-        {   // RMSNorm + gate/up + SiLU
+        {   // RMSNorm + gate/up + SiLU: this rank's slice of hb, broadcast
             Op op; memset(&op, 0, sizeof op);
             op.kind = OP_FFN; op.x = s->x; op.xt = xt; op.norm_w = L.rms_ffn_weight;
-            set_seg(op.seg[0], &L.wq_gate, nullptr, hidden, 0, 0, hbt);
-            set_seg(op.seg[1], &L.wq_up, nullptr, hidden, 0, 0, hbt);
-            const int nc[2] = {hidden, hidden};
+            set_seg(op.seg[0], &wg, nullptr, shid, 0, 0, hbt + R * shid, bc);
+            set_seg(op.seg[1], &wu, nullptr, shid, 0, 0, hbt + R * shid, bc);
+            const int nc[2] = {shid, shid};
             ok = ok && q4_op_shape(op, dim, nc, 2, true);
             ops.push_back(op);
         }
         {   // down + residual
             Op op; memset(&op, 0, sizeof op);
             op.kind = OP_GEMV; op.x = s->hb; op.xt = hbt; op.accum = 1;
-            set_seg(op.seg[0], &L.wq_down, nullptr, dim, 0, 0, xt);
-            ok = ok && q4_op_shape(op, hidden, &dim, 1, false);
+            set_seg(op.seg[0], &wd, nullptr, sdim, 0, 0, xt + R * sdim, bc);
+            ok = ok && q4_op_shape(op, hidden, &sdim, 1, false);
             ops.push_back(op);
         }
     }
-    {   // final RMSNorm + classifier; the logits stay plain fp16 (the API exposes them), so the sampler keeps its barrier
+    {   // final RMSNorm + classifier rows of this rank; the logits stay plain fp16 (the API exposes them), so the sampler keeps its barrier
         Op op; memset(&op, 0, sizeof op);
         op.kind = OP_CLS; op.x = s->x; op.xt = xt; op.norm_w = w->rms_final_weight;
-        op.seg[0].w = reinterpret_cast<const uint32_t*>(w->wcls);
-        op.seg[0].out = s->logits;
+        op.seg[0].w = reinterpret_cast<const uint32_t*>(w->wcls + (size_t)R * svoc * dim);
+        op.seg[0].out = s->logits + R * svoc;
         op.alpha = 1.0f;
-        ok = ok && cls_op_shape(op, dim, p->vocab_size, dim);
+        ok = ok && cls_op_shape(op, dim, svoc, dim);
         ops.push_back(op);
     }
     {
         Op op; memset(&op, 0, sizeof op);
         op.kind = OP_ARGMAX; op.sync_before = 1;
-        op.logits = s->logits; op.vocab = p->vocab_size;
+        op.logits = s->logits + R * svoc; op.vocab = svoc; op.vocab0 = R * svoc;
+        op.cand = (T > 1) ? cand : nullptr;
         op.tokens_out = &(s->shared_data->tokens[0]);
         op.pos_host = &(s->shared_data->pos);
         op.pos_dev = s->pos;
@@ -766,7 +806,7 @@ static bool run_network_fused(int* pPos, Config* p, RunState* s, TransformerWeig
         fprintf(stderr, "lq4: run_llama_network expects pPos == RunState::pos\n");
         exit(EXIT_FAILURE);
     }
-    launch_interp(np.plan, np.d_ops, with_argmax ? np.nops : np.nops - 1, nullptr, pPos, write_token, true, g.sm_count);
+    launch_interp(np.plan, np.d_ops, with_argmax ? np.nops : np.nops - 1, nullptr, pPos, write_token, true, g.sm_count, np.world > 1 ? &np : nullptr);
     return true;
 }
 
@@ -1077,6 +1117,45 @@ int lq4_generate_tokens(Transformer* t, Sampler* sampler, const int* prompt_toke
     const long end = time_in_ms();
     if (seconds) *seconds = (end - start) / 1000.0;
     return pos;
+}
+
+// ---------------------------------------------------------------------------------- tensor parallel (one process per GPU)
+// Rank / world of this process; call before lq4_build_transformer.  Every rank loads the whole .bin (a 7B model is 2 % of a
+// B200's memory) and streams only its column slices.
+int lq4_tp_config(int rank, int world) {
+    ensure_init();
+    if (world < 1 || world > 8 || rank < 0 || rank >= world) return 1;
+    g.tp_rank = rank; g.tp_world = world;
+    return 0;
+}
+static NetPlan* tp_plan(Transformer* t) {
+    NetPlan& np = get_net_plan(&t->config, &t->state, &t->weights);
+    return np.ok ? &np : nullptr;
+}
+// 64-byte CUDA IPC handle of this rank's tagged-activation buffer, to be sent to every other rank
+int lq4_tp_export(Transformer* t, void* handle64) {
+    ensure_init();
+    NetPlan* np = tp_plan(t);
+    if (!np) return 1;
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, np->tagged) != cudaSuccess) { set_err("cudaIpcGetMemHandle", cudaGetLastError()); return 1; }
+    static_assert(sizeof(h) == 64, "CUDA IPC handles are 64 bytes");
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+// map rank `peer`'s buffer (its exported handle) into this process; the stores of the broadcast go through this mapping
+int lq4_tp_import(Transformer* t, int peer, const void* handle64) {
+    ensure_init();
+    NetPlan* np = tp_plan(t);
+    if (!np || peer < 0 || peer >= np->world) return 1;
+    if (peer == np->rank) { np->peers[peer] = np->tagged; return 0; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { set_err("cudaIpcOpenMemHandle", e); return 1; }
+    np->peers[peer] = (uint32_t*)ptr;
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------- synthetic files

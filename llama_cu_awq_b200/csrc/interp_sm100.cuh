@@ -53,7 +53,7 @@ struct Seg {
     int ncols;
     int loff;              // element offset added to out together with pos*pos_stride (KV-cache row), see pos_stride
     int pos_stride;        // 0: out is used as is; else out += loff + pos * pos_stride  (gpu_kernels.h:224-226)
-    int pad_;
+    int bcast;             // tensor parallel: the tagged output goes to every rank's copy of the buffer (same offset), not only to ours
 };
 
 struct Op {
@@ -77,6 +77,7 @@ struct Op {
     const int* tokens;
     half* x_copy;          // CTA 0 stores the gathered embedding row here (the residual stream); op-by-op path only
     const half* res_emb;   // accumulating GEMV: the residual is this embedding table's row tokens[pos] instead of the old output
+    int res_stride;        // elements per embedding row (res_emb is already offset to this rank's first column)
     // OP_CLS
     int row_stride;        // elements between rows
     float alpha;
@@ -91,6 +92,7 @@ struct Op {
     const uint32_t* krawt;
     const uint32_t* vrawt;
     uint32_t* attn_out32;  // tagged output or nullptr
+    int attn_bcast;        // tensor parallel: broadcast attn_out32 to every rank
     const float2* rope_tab;
     int n_heads, head_size, kv_mul, kv_stride, max_seq;
     float att_alpha;
@@ -101,6 +103,8 @@ struct Op {
     volatile int* pos_host;    // SharedData::pos
     int* pos_dev;              // RunState::pos
     int write_token;
+    uint32_t* cand;        // tensor parallel: [world][2] tagged (value, index) candidates of the ranks' vocabulary slices, or nullptr
+    int vocab0;            // first vocabulary row of this rank's slice
 };
 
 static_assert(sizeof(Op) <= 512 && sizeof(Op) % 4 == 0, "Op must fit its shared-memory copy");
@@ -115,6 +119,8 @@ struct InterpParams {
     int xs_bytes;          // activation staging area (aliased with the attention scratch)
     int write_token;       // overrides Op::write_token of OP_ARGMAX when >= 0
     unsigned seq_base;     // launch counter * nops: makes the activation tags of this launch unique
+    int rank, world;       // tensor parallel: this GPU's rank; world == 1: single GPU
+    uint32_t* peers[8];    // base of every rank's tagged-activation buffer as mapped into this process (peers[rank] = ours)
     unsigned* sync;        // [2] grid barrier counter, exit counter (zero between launches)
     const int* pPos;       // device position
     unsigned long long* trace;   // optional [nops + 1] timestamps (ns): CTA 0 at the start of each op, and at the end
@@ -199,6 +205,16 @@ __device__ __forceinline__ uint32_t ld_cg_u16(const void* p) {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void st_tagged(uint32_t* p, uint32_t tag, uint32_t hbits) {
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"((tag << 16) | (hbits & 0xFFFFu)) : "memory");
+}
+// Tensor parallel: the same word goes to the same offset of every rank's buffer, over NVLink peer mappings.  Each rank then
+// polls only its own memory; no cross-GPU barrier exists anywhere.
+__device__ __forceinline__ void st_tagged_all(const InterpParams& P, uint32_t* p, uint32_t tag, uint32_t hbits) {
+    const size_t off = (size_t)(p - P.peers[P.rank]);
+    for (int r = 0; r < P.world; r++) st_tagged(P.peers[r] + off, tag, hbits);
+}
+__device__ __forceinline__ void st_tagged_maybe_all(const InterpParams& P, bool bcast, uint32_t* p, uint32_t tag, uint32_t hbits) {
+    if (bcast && P.world > 1) st_tagged_all(P, p, tag, hbits);
+    else st_tagged(p, tag, hbits);
 }
 __device__ __forceinline__ uint32_t ld_tagged_any(const uint32_t* p) {      // current word, whatever its tag (residual read by its only writer)
     uint32_t v;
@@ -784,7 +800,7 @@ __device__ void run_q4(Ctx& c, const Op& op, const NormRegs& nr) {
                 val = __fmul_rn(val, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-val))));
                 val = __fmul_rn(val, v1);
                 const uint32_t hb = f2h_bits(val);
-                if (op.seg[0].out32 != nullptr) st_tagged(op.seg[0].out32 + col, c.tag_out, hb);
+                if (op.seg[0].out32 != nullptr) st_tagged_maybe_all(*c.P, op.seg[0].bcast != 0, op.seg[0].out32 + col, c.tag_out, hb);
                 else op.seg[0].out[col] = __ushort_as_half((unsigned short)hb);
             } else {
                 const Seg& sg = op.seg[seg];
@@ -794,7 +810,7 @@ __device__ void run_q4(Ctx& c, const Op& op, const NormRegs& nr) {
                 if (op.accum) {
                     uint32_t o0, o1;
                     if (op.res_emb != nullptr) {                 // first layer: the residual is the embedding row itself
-                        const half* e = op.res_emb + (size_t)op.tokens[c.pos] * sg.ncols + col;
+                        const half* e = op.res_emb + (size_t)op.tokens[c.pos] * op.res_stride + col;
                         o0 = ldg_stream_u16(e); o1 = ldg_stream_u16(e + 1);
                     } else if (sg.out32 != nullptr) {
                         o0 = ld_tagged_any(sg.out32 + col) & 0xFFFFu; o1 = ld_tagged_any(sg.out32 + col + 1) & 0xFFFFu;
@@ -805,7 +821,10 @@ __device__ void run_q4(Ctx& c, const Op& op, const NormRegs& nr) {
                     s1 = s1 + h2f_bits(o1);
                 }
                 const uint32_t h0 = f2h_bits(s0), h1 = f2h_bits(s1);
-                if (sg.out32 != nullptr) { st_tagged(sg.out32 + col, c.tag_out, h0); st_tagged(sg.out32 + col + 1, c.tag_out, h1); }
+                if (sg.out32 != nullptr) {
+                    st_tagged_maybe_all(*c.P, sg.bcast != 0, sg.out32 + col, c.tag_out, h0);
+                    st_tagged_maybe_all(*c.P, sg.bcast != 0, sg.out32 + col + 1, c.tag_out, h1);
+                }
                 if (dst != nullptr) { dst[col] = __ushort_as_half((unsigned short)h0); dst[col + 1] = __ushort_as_half((unsigned short)h1); }
             }
         }
@@ -1127,7 +1146,7 @@ __device__ void run_attn_t(Ctx& c, const Op& op, bool prefetched) {
             for (int o = 1; o < 32; o <<= 1)
 #pragma unroll
                 for (int w = 0; w < 32; w += 2 * o) v[w] = v[w] + v[w + o];
-            if (op.attn_out32 != nullptr) st_tagged(op.attn_out32 + (size_t)h * hs + i, c.tag_out, f2h_bits(v[0]));
+            if (op.attn_out32 != nullptr) st_tagged_maybe_all(*c.P, op.attn_bcast != 0, op.attn_out32 + (size_t)h * hs + i, c.tag_out, f2h_bits(v[0]));
             else op.attn_out[(size_t)h * hs + i] = __float2half_rn(v[0]);
         }
         named_bar(kBarAll, nt);
@@ -1188,6 +1207,19 @@ __device__ void run_argmax(Ctx& c, const Op& op, int write_token) {
     if (c.ctid == 0) {
         for (int w = 1; w < c.nwc; w++)
             if (smax[w] > max_val || (smax[w] == max_val && sidx[w] < max_pos)) { max_val = smax[w]; max_pos = sidx[w]; }
+        if (op.cand != nullptr && c.P->world > 1) {
+            // tensor parallel: every rank publishes the best of its vocabulary slice to all ranks, then picks the global
+            // winner itself (largest value, lowest index on ties): all ranks write the same token without a host round trip
+            const int rank = c.P->rank, world = c.P->world;
+            st_tagged_all(*c.P, op.cand + 2 * rank, c.tag_out, f2h_bits(max_val));
+            st_tagged_all(*c.P, op.cand + 2 * rank + 1, c.tag_out, (uint32_t)(max_pos + op.vocab0));
+            max_val = -INFINITY; max_pos = 0x7fffffff;
+            for (int r = 0; r < world; r++) {
+                const float v = h2f_bits(poll1(op.cand + 2 * r, c.tag_out));
+                const int idx = (int)poll1(op.cand + 2 * r + 1, c.tag_out);
+                if (v > max_val || (v == max_val && idx < max_pos)) { max_val = v; max_pos = idx; }
+            }
+        }
         int token_pos = c.pos + 1;     // SharedData::pos and RunState::pos move together (gpu_kernels.h:486-491); no PCIe read
         if (write_token) op.tokens_out[token_pos] = max_pos;
         __threadfence_system();

@@ -1,0 +1,54 @@
+"""Tensor-parallel decode: the ranks' greedy token ids must equal the single-GPU engine's, which are
+bit-identical to the reference's.  Needs >= 2 GPUs (gpurun --gpus 2); skipped otherwise."""
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("cfg_name,world", [("TINY", 2), ("SMALL", 2), ("TINY_GQA", 2)])
+def test_tp_tokens_equal_single_gpu(cfg_name, world):
+    if _ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import llama_cu_awq_b200 as E
+    lib = E.lib()
+    assert lib.lq4_init(0) == 0
+    cfg = getattr(H, cfg_name)
+    steps, prompt = 48, [1, 35, 72]
+    with tempfile.TemporaryDirectory() as d:
+        path, outp = os.path.join(d, "m.bin"), os.path.join(d, "tp.json")
+        c = E.Config(**cfg)
+        assert lib.lq4_write_synth_model(path.encode(), C.byref(c), 2025) == os.path.getsize(path)
+        # single GPU
+        t = E.Transformer()
+        assert lib.lq4_build_transformer(C.byref(t), path.encode(), 0) == 0
+        s = E.Sampler()
+        lib.lq4_build_sampler(C.byref(s), cfg["vocab_size"], 0.0, 0.9, 1)
+        ptoks = (C.c_int * len(prompt))(*prompt)
+        out = (C.c_int * steps)()
+        secs = C.c_double(0)
+        n = lib.lq4_generate_tokens(C.byref(t), C.byref(s), ptoks, len(prompt), steps, out, C.byref(secs), 1)
+        single = [int(out[i]) for i in range(n)]
+        lib.lq4_free_transformer(C.byref(t))
+        # tensor parallel, one process per GPU
+        env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                            "--master-port", "29533", os.path.join(H.ROOT, "tests", "tp_worker.py"), path, str(steps), outp,
+                            ",".join(map(str, prompt))], capture_output=True, text=True, timeout=300, env=env)
+        assert r.returncode == 0, (r.stdout[-1500:] + r.stderr[-1500:])
+        res = json.load(open(outp))
+        assert res["all_equal"], "ranks disagree on the token ids"
+        assert res["tokens"] == single, f"TP={world} ids differ from single GPU"
