@@ -204,6 +204,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--model", default="7b")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parallelism", default="replicas", choices=["replicas", "tp"],
+                    help="N>1: independent replicas (weak scaling, default) or tensor-parallel decode of ONE stream (strong scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -224,6 +226,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = E.lib()
     assert lib.lq4_init(local_rank) == 0
+    tp = world > 1 and args.parallelism == "tp"
+    if tp:
+        assert lib.lq4_tp_config(rank, world) == 0
     cfg = model_cfg(args.model)
     K = max(1, min(args.steps, cfg["seq_len"] - 1))
     W = max(3, args.warmup)
@@ -235,6 +240,8 @@ def main():
     lib.lq4_build_transformer(C.byref(t), path.encode(), 0)
     s = E.Sampler()
     lib.lq4_build_sampler(C.byref(s), cfg["vocab_size"], 0.0, 0.9, 1)
+    if tp:
+        E.tp_connect(lib, t, rank, world)     # CUDA IPC handles of the ranks' activation buffers, exchanged over torch.distributed
     stream = torch.cuda.ExternalStream(lib.lq4_get_stream())
     bos = (C.c_int * 1)(1)
 
@@ -243,7 +250,9 @@ def main():
         for i in range(n_steps):
             lib.lq4_enqueue_step(C.byref(t), C.byref(s), i + 1, 1)
 
-    # ---- warm-up (also captures the graphs for every bin the timed run touches) ----
+    # ---- warm-up ----
+    if world > 1:
+        dist.barrier()
     enqueue(min(cfg["seq_len"] - 1, max(W, 130 if K > 128 else W)))
     if K > 256:
         enqueue(K)
@@ -282,6 +291,7 @@ def main():
     assert list(out)[1:n] == tokens_dev[1:n], "pipelined host API and raw enqueue disagree on token ids"
     if world > 1:
         e2e_val = (n - 1) / max_over_ranks(secs.value, world)
+    units = 1 if tp else world        # tensor parallel: all ranks decode ONE stream; replicas: one stream each
 
     # ---- roofline ----
     # The decode step is ONE launch of the persistent kernel (interp_kernel), so the dominant kernel's launch
@@ -291,7 +301,7 @@ def main():
     d, h, L = cfg["dim"], cfg["hidden_dim"], cfg["n_layers"]
     wbytes = E.weight_bytes_per_token(cfg)
     kvbytes = sum(E.kv_bytes_at(cfg, p) for p in range(K)) / K
-    step_gbs = (wbytes + kvbytes) / (ms / K * 1e-3) / 1e9
+    step_gbs = (wbytes + kvbytes) / (ms / K * 1e-3) / 1e9 / (world if tp else 1)     # per GPU: each rank streams 1/world of the bytes
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "step_traffic.json")
     if os.path.exists(tpath):
@@ -322,15 +332,15 @@ def main():
     ach = ffn_bytes / (ffn_us * 1e-6) / 1e9
     roofline_ffn = {"bound": "hbm", "kernel": "interp_kernel, single op lq4_ffn_matvec_silu (K=%d N=%d), launch overhead included" % (d, h),
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "bytes_per_launch": ffn_bytes, "us_per_launch": ffn_us}
-    value = aggregate_throughput(K, ms * 1e-3, 1) * world      # ms is already the max over ranks
+    value = aggregate_throughput(K, ms * 1e-3, 1) * units      # ms is already the max over ranks
 
     line = {"metric": "decode tokens/sec (seq_len=1)", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if tp else "weak", "vs_baseline": None,
             "dtype": "int4 weights, fp16 storage, fp32 accumulate", "data": "synthetic",
             "config": {"workload": f"Llama-2-{args.model.upper()} w4-g128 random-init .bin, greedy decode -n {K}, batch 1",
-                       "l2": "inputs larger than L2 (3.6 GB of weights per step)", "parallelism": "replicas" if world > 1 else "1 GPU"},
+                       "l2": "inputs larger than L2 (3.6 GB of weights per step)", "parallelism": ("tp%d" % world if tp else "replicas x%d" % world) if world > 1 else "1 GPU"},
             "clocks": clk,
-            "e2e": {"value": (e2e_val * world) if e2e_val else None, "unit": "tokens/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 8,
+            "e2e": {"value": (e2e_val * units) if e2e_val else None, "unit": "tokens/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 8,
                     "how": "lq4_generate_tokens(host prompt ids -> host ids), wall clock of its loop, pipelined launch; per step the kernel "
                            "reads the token id from pinned host memory and writes the new id and position back to it"},
             "gpu_launches": K,
