@@ -19,7 +19,7 @@ def _ngpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("cfg_name,world", [("TINY", 2), ("SMALL", 2), ("TINY_GQA", 2)])
+@pytest.mark.parametrize("cfg_name,world", [("TINY", 2), ("SMALL", 2), ("TINY_GQA", 2), ("SMALL", 4), ("SMALL", 8)])
 def test_tp_tokens_equal_single_gpu(cfg_name, world):
     if _ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
