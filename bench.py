@@ -332,6 +332,24 @@ def main():
     ach = ffn_bytes / (ffn_us * 1e-6) / 1e9
     roofline_ffn = {"bound": "hbm", "kernel": "interp_kernel, single op lq4_ffn_matvec_silu (K=%d N=%d), launch overhead included" % (d, h),
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "bytes_per_launch": ffn_bytes, "us_per_launch": ffn_us}
+    # BASELINE.json configs[0]: single INT4 GEMV M=1 K=N=4096 g128 (the o-projection), one matrix per layer in rotation
+    # (32 x 8.7 MB > L2 would be needed for a cold number; 7B has exactly 32 such matrices = 279 MB)
+    gemv_bytes = d * (E.packed_weight_height(d) * 4 + E.packed_zeros_height(d) * 4 + E.num_groups(d) * 2)
+    for l in range(L):
+        lib.lq4_matmul_q4(t.state.x, t.state.xb, C.byref(layers[l].wq_o), d, d, 0, -1, None)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+    for _ in range(reps):
+        for l in range(L):
+            lib.lq4_matmul_q4(t.state.x, t.state.xb, C.byref(layers[l].wq_o), d, d, 0, -1, None)
+    with torch.cuda.stream(stream):
+        ev1.record(stream)
+    torch.cuda.synchronize()
+    gemv_us = ev0.elapsed_time(ev1) * 1000.0 / (reps * L)
+    gemv_op = {"kernel": "interp_kernel, single op lq4_matmul_q4 (K=N=%d g128), launch overhead included" % d, "bytes_per_launch": gemv_bytes,
+               "us_per_launch": gemv_us, "achieved": gemv_bytes / (gemv_us * 1e-6) / 1e9, "unit": "GB/s", "peak": peak,
+               "frac": gemv_bytes / (gemv_us * 1e-6) / 1e9 / peak}
     value = aggregate_throughput(K, ms * 1e-3, 1) * units      # ms is already the max over ranks
 
     line = {"metric": "decode tokens/sec (seq_len=1)", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -345,7 +363,8 @@ def main():
                            "reads the token id from pinned host memory and writes the new id and position back to it"},
             "gpu_launches": K,
             "roofline": roofline,
-            "roofline_ffn_op": roofline_ffn}
+            "roofline_ffn_op": roofline_ffn,
+            "gemv_4096_op": gemv_op}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline_sample(path, cfg, 1)
