@@ -938,30 +938,65 @@ __host__ __device__ __forceinline__ int attn_buf_bytes(int hs) {
 __host__ __device__ __forceinline__ int attn_fixed_bytes(int hs, int max_seq) { return ((3 * hs + ((max_seq + 3) & ~3)) * 4 + 127) & ~127; }
 
 // rows [row0, row0 + nrows) of one head (hs halfs each, kv_stride apart) -> shared memory, row-major
-__device__ __forceinline__ void attn_load_tile(const Ctx& c, uint32_t dst, const half* base, int kv_stride, int hs, int row0, int nrows) {
+// One batch of a tile copy: up to three 16-byte vectors per thread in flight (a 64 x 128 tile is one batch for 342+ threads).
+constexpr int kAttnVecs = 3;
+struct TileRegs {
+    uint4 v[kAttnVecs];
+};
+__device__ __forceinline__ void attn_tile_ld(const Ctx& c, TileRegs& t, const half* base, int kv_stride, int hs, int row0, int nrows, int first) {
     const int vsh = (hs == 128) ? 4 : (hs == 64) ? 3 : 2;  // log2(16-byte vectors per row)
     const int total = nrows << vsh;
     const half* src = base + (size_t)row0 * kv_stride;
-#pragma unroll 1
-    for (int b0 = c.ctid; b0 < total; b0 += 2 * c.nthreads) {
-        const int i0 = b0, i1 = b0 + c.nthreads;
-        const bool p1 = i1 < total;
-        const int r0 = i0 >> vsh, c0 = i0 & ((1 << vsh) - 1), r1 = p1 ? (i1 >> vsh) : r0, c1 = p1 ? (i1 & ((1 << vsh) - 1)) : c0;
-        const uint4 v0 = ld_cg_v4(src + (size_t)r0 * kv_stride + c0 * 8);
-        const uint4 v1 = ld_cg_v4(src + (size_t)r1 * kv_stride + c1 * 8);
-        sts_v4_u32(dst + i0 * 16, v0);
-        if (p1) sts_v4_u32(dst + i1 * 16, v1);
+#pragma unroll
+    for (int r = 0; r < kAttnVecs; r++) {
+        const int idx = first + c.ctid + r * c.nthreads;
+        t.v[r] = make_uint4(0, 0, 0, 0);
+        if (idx < total) t.v[r] = ld_cg_v4(src + (size_t)(idx >> vsh) * kv_stride + (idx & ((1 << vsh) - 1)) * 8);
     }
 }
-// before the grid barrier: first K and V tile of this CTA's (first) head
+__device__ __forceinline__ void attn_tile_st(const Ctx& c, const TileRegs& t, uint32_t dst, int hs, int nrows, int first) {
+    const int vsh = (hs == 128) ? 4 : (hs == 64) ? 3 : 2;
+    const int total = nrows << vsh;
+#pragma unroll
+    for (int r = 0; r < kAttnVecs; r++) {
+        const int idx = first + c.ctid + r * c.nthreads;
+        if (idx < total) sts_v4_u32(dst + idx * 16, t.v[r]);
+    }
+}
+// rows [row0, row0 + nrows) of one head (hs halfs each, kv_stride apart) -> shared memory, row-major
+__device__ __forceinline__ void attn_load_tile(const Ctx& c, uint32_t dst, const half* base, int kv_stride, int hs, int row0, int nrows) {
+    const int vsh = (hs == 128) ? 4 : (hs == 64) ? 3 : 2;
+    const int total = nrows << vsh;
+#pragma unroll 1
+    for (int first = 0; first < total; first += kAttnVecs * c.nthreads) {
+        TileRegs t;
+        attn_tile_ld(c, t, base, kv_stride, hs, row0, nrows, first);
+        attn_tile_st(c, t, dst, hs, nrows, first);
+    }
+}
+// two tiles at once: both trips to L2 overlap
+__device__ __forceinline__ void attn_load_tiles2(const Ctx& c, uint32_t dst0, uint32_t dst1, const half* base, int kv_stride, int hs, int n0, int n1) {
+    const int vsh = (hs == 128) ? 4 : (hs == 64) ? 3 : 2;
+    const int total = (n0 > n1 ? n0 : n1) << vsh;
+#pragma unroll 1
+    for (int first = 0; first < total; first += kAttnVecs * c.nthreads) {
+        TileRegs t0, t1;
+        attn_tile_ld(c, t0, base, kv_stride, hs, 0, n0, first);
+        attn_tile_ld(c, t1, base, kv_stride, hs, kAttnTile, n1, first);
+        attn_tile_st(c, t0, dst0, hs, n0, first);
+        attn_tile_st(c, t1, dst1, hs, n1, first);
+    }
+}
+// Before the op's inputs are waited for: the first two K tiles of this CTA's (first) head.  Rows t < pos were written
+// by earlier launches, so they depend on nothing in this one.
 __device__ void attn_prefetch(const Ctx& c, const Op& op) {
     const int h = blockIdx.x, hs = op.head_size;
-    if (h >= op.n_heads || (hs & 7)) return;
+    if (h >= op.n_heads) return;
     const int kvh = h / op.kv_mul;
-    const int nrows = c.pos < kAttnTile ? c.pos : kAttnTile;
     const uint32_t bufA = c.sm.xs + attn_fixed_bytes(hs, op.max_seq), bufB = bufA + attn_buf_bytes(hs);
-    attn_load_tile(c, bufA, op.kcache + (size_t)kvh * hs, op.kv_stride, hs, 0, nrows);
-    attn_load_tile(c, bufB, op.vcache + (size_t)kvh * hs, op.kv_stride, hs, 0, nrows);
+    const half* kb = op.kcache + (size_t)kvh * hs;
+    const int n0 = c.pos < kAttnTile ? c.pos : kAttnTile, n1 = c.pos - kAttnTile < kAttnTile ? c.pos - kAttnTile : kAttnTile;
+    attn_load_tiles2(c, bufA, bufB, kb, op.kv_stride, hs, n0, n1 > 0 ? n1 : 0);
 }
 
 template <int NSER>
@@ -1032,14 +1067,15 @@ __device__ void run_attn_t(Ctx& c, const Op& op, bool prefetched) {
 #pragma unroll 1
         for (int tile0 = 0; tile0 < pos; tile0 += kAttnTile) {
             const int nrows = (pos - tile0 < kAttnTile) ? pos - tile0 : kAttnTile;
-            if (!(have_tile0 && tile0 == 0)) {
+            const uint32_t kbuf = (tile0 == kAttnTile) ? bufB : bufA;     // tiles 0 and 1 have their own buffer (prefetched), later ones reuse bufA
+            if (!(have_tile0 && tile0 <= kAttnTile)) {
                 named_bar(kBarAll, nt);                    // the previous tile is no longer read
-                attn_load_tile(c, bufA, kbase, op.kv_stride, hs, tile0, nrows);
+                attn_load_tile(c, kbuf, kbase, op.kv_stride, hs, tile0, nrows);
             }
             named_bar(kBarAll, nt);                        // tile (and, first time round, qs / krow / vrow) visible
 #pragma unroll 2
             for (int r = warp; r < nrows; r += c.nwc) {
-                const uint32_t row = bufA + (uint32_t)r * hs * 2;
+                const uint32_t row = kbuf + (uint32_t)r * hs * 2;
                 float sum = 0.0f;
 #pragma unroll
                 for (int i = 0; i < NS; i++) sum = __fmaf_rn(h2f_bits(lds_u16(row + (i * 32 + lane) * 2)), qs[i * 32 + lane], sum);
@@ -1059,8 +1095,7 @@ __device__ void run_attn_t(Ctx& c, const Op& op, bool prefetched) {
         }
         // second V tile (if any) goes to bufA while the softmax runs: K is dead from here on
         const int v1rows = (pos > kAttnTile) ? ((pos - kAttnTile < kAttnTile) ? pos - kAttnTile : kAttnTile) : 0;
-        if (!have_tile0) attn_load_tile(c, bufB, vbase, op.kv_stride, hs, 0, pos < kAttnTile ? pos : kAttnTile);
-        if (v1rows > 0) attn_load_tile(c, bufA, vbase, op.kv_stride, hs, kAttnTile, v1rows);
+        attn_load_tiles2(c, bufB, bufA, vbase, op.kv_stride, hs, pos < kAttnTile ? pos : kAttnTile, v1rows);
         named_bar(kBarAll, nt);
         trace_mark(c, 3);
         // ---- softmax (idle reference threads seed the max with 0, gpu_kernels.h:374) ----
@@ -1290,8 +1325,8 @@ __global__ void __launch_bounds__(32 * (kMaxConsumerWarps + 1), 1) interp_kernel
         c.tag_in = ((P.seq_base + (unsigned)o) & 0x7FFFu) | 0x8000u;           // the previous op's
         NormRegs nr;
         load_norm_regs(c, ops[o], nr);             // in flight while the grid barrier completes
-        const bool attn_pref = (ops[o].kind == OP_ATTN) && sync_before;
-        if (attn_pref) attn_prefetch(c, ops[o]);   // K / V rows of earlier positions do not depend on it either
+        const bool attn_pref = (ops[o].kind == OP_ATTN);
+        if (attn_pref) attn_prefetch(c, ops[o]);   // K rows of earlier positions do not depend on this launch at all
         if (sync_before) {
             c.nsync++;
             if (c.ctid == 0) grid_wait(P.sync, c.nsync * gridDim.x);
