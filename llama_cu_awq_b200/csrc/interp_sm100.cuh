@@ -489,33 +489,49 @@ __device__ __forceinline__ void trace_mark(const Ctx& c, int k) {
 // aggregates in order.  x is the raw fp16 vector already in shared memory.  All consumer threads call this;
 // returns the scale in every thread.
 __device__ float cta_rms_scale(Ctx& c, uint32_t xraw, int size) {
+    // A half-warp stands for one virtual warp: thread j holds the chains of virtual lanes 2j and 2j+1 (one 32-bit load per
+    // pair), so the first level of the cub tree is a local add and the other four are a butterfly over 16 threads.
     const int ept = (size - 1) / 1024 + 1;
-    for (int vw0 = c.warp; vw0 < 32; vw0 += 4 * c.nwc) {      // up to four virtual warps per pass, chains interleaved
-        float ss[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    const int h = c.lane >> 4, j = c.lane & 15;
+    const uint32_t red = c.sm.bars + kRedOffset;
+    for (int vw = 2 * c.warp + h; vw < 32; vw += 2 * c.nwc) {      // both half-warps of a warp run the same number of passes
+        float sa = 0.0f, sb = 0.0f;
         for (int i = 0; i < ept; i++) {
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-                const int idx = (vw0 + r * c.nwc) * 32 + c.lane + i * 1024;
-                if (vw0 + r * c.nwc < 32 && idx < size) {
-                    const float v = h2f_bits(lds_u16(xraw + idx * 2));
-                    ss[r] = __fmaf_rn(v, v, ss[r]);
-                }
+            const int idx = vw * 32 + 2 * j + i * 1024;
+            if (idx + 1 < size) {
+                const uint32_t w = lds_u32(xraw + idx * 2);
+                const float a = h2f_bits(w & 0xFFFFu), b = h2f_bits(w >> 16);
+                sa = __fmaf_rn(a, a, sa);
+                sb = __fmaf_rn(b, b, sb);
+            } else if (idx < size) {
+                const float a = h2f_bits(lds_u16(xraw + idx * 2));
+                sa = __fmaf_rn(a, a, sa);
             }
         }
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const float tot = warp_tree_sum(ss[r]);
-            if (c.lane == 0 && vw0 + r * c.nwc < 32) c.red[vw0 + r * c.nwc] = tot;
-        }
+        float v = sa + sb;
+        v = v + __shfl_xor_sync(0xffffffffu, v, 1);
+        v = v + __shfl_xor_sync(0xffffffffu, v, 2);
+        v = v + __shfl_xor_sync(0xffffffffu, v, 4);
+        v = v + __shfl_xor_sync(0xffffffffu, v, 8);
+        if (j == 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(red + vw * 4), "f"(v) : "memory");
     }
     named_bar(kBarAll, c.nthreads);
-    float tot = c.red[0];
+    float tot;
+    {
+        float r[32];
 #pragma unroll
-    for (int w = 1; w < 32; w++) tot = tot + c.red[w];
-    tot = __fdiv_rn(tot, (float)size);
+        for (int q = 0; q < 8; q++) {
+            const uint4 t = lds_v4(red + q * 16);
+            r[4 * q] = __uint_as_float(t.x); r[4 * q + 1] = __uint_as_float(t.y); r[4 * q + 2] = __uint_as_float(t.z); r[4 * q + 3] = __uint_as_float(t.w);
+        }
+        tot = r[0];
+#pragma unroll
+        for (int w = 1; w < 32; w++) tot = tot + r[w];       // thread 0 of the reference adds the warp aggregates in order
+    }
+    tot = ((size & (size - 1)) == 0) ? __fmul_rn(tot, 1.0f / (float)size) : __fdiv_rn(tot, (float)size);   // exact either way
     tot = tot + 1e-5f;
     tot = __fdiv_rn(1.0f, __fsqrt_rn(tot));
-    named_bar(kBarAll, c.nthreads);   // red may be reused
+    // no trailing barrier: the scratch is next written in a later op, behind that op's opening barrier
     return tot;
 }
 
