@@ -52,6 +52,7 @@ struct NetPlan {
     uint32_t* tagged = nullptr;   // flag-in-data activation vectors of the fused step: x | xb | hb | q | k (un-rotated) | v | argmax candidates
     uint32_t* peers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // every rank's `tagged`, mapped here
     int world = 1, rank = 0;
+    unsigned seq_base = 0;        // activation-tag base of the last launch of this plan
     std::vector<char> key;     // Config + pointers the table was built from
     bool ok = false;           // false: some shape is not supported by the persistent kernel
 };
@@ -71,7 +72,6 @@ struct Engine {
     std::map<RopeKey, float2*> rope_tabs;
     std::map<const void*, NetPlan> nets;
     unsigned* sync = nullptr;
-    unsigned long long launch_seq = 1;   // persistent-kernel launches so far (activation tags)
     int tp_rank = 0, tp_world = 1;       // tensor parallel: one process per GPU, this one's rank
     int opt_trace = 0;      // record per-op timestamps of fused steps (development aid)
     int opt_trace_op = -1;  // op whose phases are recorded per CTA
@@ -299,14 +299,23 @@ QWeight slice_cols(const QWeight& w, int K, int c0) {
 }
 
 void launch_interp(const Plan& pl, const Op* d_ops, int nops, const Op* one, const int* pPos, int write_token,
-                   bool cooperative, int grid, const NetPlan* tp = nullptr) {
+                   bool cooperative, int grid, const NetPlan* tp_or_plan = nullptr) {
     InterpParams P;
     memset(&P, 0, sizeof P);
     P.ops = d_ops; P.nops = nops;
     P.nwc = pl.nwc; P.nslots = pl.nslots; P.slot_bytes = pl.slot_bytes; P.meta_bytes = pl.meta_bytes; P.xs_bytes = pl.xs_bytes;
     P.write_token = write_token;
     P.sync = g.sync; P.pPos = pPos;
-    P.seq_base = (unsigned)((g.launch_seq++ * (unsigned long long)std::max(nops, 1)) & 0x3FFFFFFFull);
+    // Activation tags: consecutive launches over the same buffers must never share a tag.  Each plan advances its own base by
+    // its op count per launch, so two consecutive launches differ by nops (mod 2^15), whatever else ran in between; all ranks
+    // of a tensor-parallel group launch in lockstep and therefore agree on it.
+    P.seq_base = 0;
+    if (tp_or_plan != nullptr) {
+        NetPlan* np = const_cast<NetPlan*>(tp_or_plan);
+        np->seq_base = (np->seq_base + (unsigned)np->nops) & 0x3FFFFFFFu;
+        P.seq_base = np->seq_base;
+    }
+    const NetPlan* tp = (tp_or_plan != nullptr && tp_or_plan->world > 1) ? tp_or_plan : nullptr;
     P.rank = 0; P.world = 1;
     if (tp != nullptr) {
         P.rank = tp->rank; P.world = tp->world;
@@ -806,7 +815,7 @@ static bool run_network_fused(int* pPos, Config* p, RunState* s, TransformerWeig
         fprintf(stderr, "lq4: run_llama_network expects pPos == RunState::pos\n");
         exit(EXIT_FAILURE);
     }
-    launch_interp(np.plan, np.d_ops, with_argmax ? np.nops : np.nops - 1, nullptr, pPos, write_token, true, g.sm_count, np.world > 1 ? &np : nullptr);
+    launch_interp(np.plan, np.d_ops, with_argmax ? np.nops : np.nops - 1, nullptr, pPos, write_token, true, g.sm_count, &np);
     return true;
 }
 
