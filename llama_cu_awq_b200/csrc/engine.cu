@@ -53,6 +53,7 @@ struct NetPlan {
     uint32_t* peers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // every rank's `tagged`, mapped here
     int world = 1, rank = 0;
     unsigned seq_base = 0;        // activation-tag base of the last launch of this plan
+    const int* tokens = nullptr;  // SharedData::tokens of the RunState the plan was built for
     std::vector<char> key;     // Config + pointers the table was built from
     bool ok = false;           // false: some shape is not supported by the persistent kernel
 };
@@ -314,6 +315,7 @@ void launch_interp(const Plan& pl, const Op* d_ops, int nops, const Op* one, con
         NetPlan* np = const_cast<NetPlan*>(tp_or_plan);
         np->seq_base = (np->seq_base + (unsigned)np->nops) & 0x3FFFFFFFu;
         P.seq_base = np->seq_base;
+        P.tokens = np->tokens;
     }
     const NetPlan* tp = (tp_or_plan != nullptr && tp_or_plan->world > 1) ? tp_or_plan : nullptr;
     P.rank = 0; P.world = 1;
@@ -686,6 +688,7 @@ static NetPlan& get_net_plan(Config* p, RunState* s, TransformerWeights* w) {
     // bit-identical to one GPU.  The slices are expressed by offsetting the pointers: the kernel sees smaller matrices.
     const int T = g.tp_world, R = g.tp_rank;
     np.world = T; np.rank = R;
+    np.tokens = s->shared_data->tokens;
     if (T > 1 && (p->n_heads % T || p->n_kv_heads % T || (dim / T) % 8 || (hidden / T) % 8 || (kv_dim / T) % 8 || (p->vocab_size / T) % 8 ||
                   p->vocab_size % T || p->vocab_size > 65535 || T > 8)) return np;
     const int sdim = dim / T, shid = hidden / T, skv = kv_dim / T, sheads = p->n_heads / T, svoc = p->vocab_size / T;
@@ -1029,7 +1032,11 @@ void lq4_free_transformer(Transformer* t) {
     RunState* s = &t->state;
     cudaStreamSynchronize(g.stream);
     auto np = g.nets.find((const void*)s);
-    if (np != g.nets.end()) { cudaFree(np->second.d_ops); cudaFree(np->second.tagged); g.nets.erase(np); }
+    if (np != g.nets.end()) {
+        for (int r = 0; r < np->second.world; r++)
+            if (r != np->second.rank && np->second.peers[r] != nullptr) cudaIpcCloseMemHandle(np->second.peers[r]);
+        cudaFree(np->second.d_ops); cudaFree(np->second.tagged); g.nets.erase(np);
+    }
     cudaFree(s->x); cudaFree(s->xb); cudaFree(s->pos); cudaFree(s->hb); cudaFree(s->q); cudaFree(s->att);
     cudaFree(s->logits); cudaFree(s->key_cache); cudaFree(s->value_cache); cudaFreeHost(s->shared_data);
     if (s->logits_array) cudaFree(s->logits_array);

@@ -123,6 +123,7 @@ struct InterpParams {
     uint32_t* peers[8];    // base of every rank's tagged-activation buffer as mapped into this process (peers[rank] = ours)
     unsigned* sync;        // [2] grid barrier counter, exit counter (zero between launches)
     const int* pPos;       // device position
+    const int* tokens;     // pinned-host token ring of the step (SharedData::tokens): read ONCE per launch, at its start
     unsigned long long* trace;   // optional [nops + 1] timestamps (ns): CTA 0 at the start of each op, and at the end
     int trace_op;                // op whose phases every CTA records at trace[2048 + cta * 8 + k]
     Op one;                // inline single op (operator API)
@@ -134,7 +135,7 @@ constexpr int kBarAll = 13;        // named barrier: all consumer warps
 constexpr int kCtrlBytes = 4096;   // mbarriers (first 2 KB) + reduction scratch (at 3 KB)
 constexpr int kRedOffset = 3072;
 constexpr unsigned kSpinLimit = 1u << 24;
-constexpr unsigned long long kWaitLimitNs = 2000000000ull;   // a wait longer than 2 s is a protocol bug: trap
+constexpr unsigned long long kWaitLimitNs = 5000000000ull;   // a wait longer than 5 s is a protocol bug (or a dead peer): trap
 constexpr int kLapOffset = 2048;   // per-slot release counters (up to 120 words)
 constexpr int kOpOffset = 2560;    // the current op, copied from the table (512 bytes)
 // ------------------------------------------------------------------------------------------------
@@ -470,6 +471,7 @@ struct Ctx {
     int nwc, nthreads;        // consumer warps / threads
     int warp, lane, ctid;
     int pos;
+    int token;                // tokens[pos], fetched over PCIe at the start of the launch
     unsigned qbase;           // ring chunks of all ops before the current one (this CTA)
     unsigned mcount;          // INT4 ops so far (scale/zero buffer = mcount & 1)
     int meta_pending;         // scale/zero buffer to hand back to the producer once every warp has left the op, or -1
@@ -592,7 +594,7 @@ __device__ void stage_x_pairs(Ctx& c, const Op& op, const NormRegs& nr) {
     const int K = op.K;
     const half* xin = op.x;
     if (op.emb != nullptr) {
-        const int token = op.tokens[c.pos];
+        const int token = (op.tokens == c.P->tokens) ? c.token : op.tokens[c.pos];
         xin = op.emb + (size_t)token * K;
     }
     const bool norm = (op.norm_w != nullptr);
@@ -826,7 +828,7 @@ __device__ void run_q4(Ctx& c, const Op& op, const NormRegs& nr) {
                 if (op.accum) {
                     uint32_t o0, o1;
                     if (op.res_emb != nullptr) {                 // first layer: the residual is the embedding row itself
-                        const half* e = op.res_emb + (size_t)op.tokens[c.pos] * op.res_stride + col;
+                        const half* e = op.res_emb + (size_t)((op.tokens == c.P->tokens) ? c.token : op.tokens[c.pos]) * op.res_stride + col;
                         o0 = ldg_stream_u16(e); o1 = ldg_stream_u16(e + 1);
                     } else if (sg.out32 != nullptr) {
                         o0 = ld_tagged_any(sg.out32 + col) & 0xFFFFu; o1 = ld_tagged_any(sg.out32 + col + 1) & 0xFFFFu;
@@ -1319,6 +1321,7 @@ __global__ void __launch_bounds__(32 * (kMaxConsumerWarps + 1), 1) interp_kernel
     c.scratch = smem + kCtrlBytes;
     c.nwc = P.nwc; c.nthreads = P.nwc * 32; c.warp = warp; c.lane = lane; c.ctid = threadIdx.x;
     c.pos = (P.pPos != nullptr) ? *P.pPos : 0;
+    c.token = (P.tokens != nullptr) ? P.tokens[c.pos] : 0;
     c.qbase = 0; c.mcount = 0; c.meta_pending = -1; c.nsync = 0; c.tr = nullptr; c.tag_in = c.tag_out = 0;
 
     const Op& op = *reinterpret_cast<const Op*>(smem + kOpOffset);
