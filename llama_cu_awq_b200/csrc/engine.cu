@@ -40,7 +40,7 @@ struct RopeKey {
 
 // launch geometry of the persistent kernel (shared-memory map of interp_sm100.cuh)
 struct Plan {
-    int nwc = 0, nslots = 0, slot_bytes = 0, meta_bytes = 0, xs_bytes = 0;
+    int nwc = 0, ring_bytes = 0, meta_bytes = 0, xs_bytes = 0;
     size_t smem = 0;
 };
 
@@ -203,20 +203,15 @@ int attn_scratch_bytes(int head_size, int max_seq) { return attn_fixed_bytes(hea
 
 // Shared-memory plan for `nwc` consumer warps: a staging area of `xs` bytes (activations / attention scratch),
 // `meta` bytes of scales / zero points and as many ring slots of `slot` bytes as fit.
-bool make_plan(Plan& pl, int nwc, int xs, int meta, int slot) {
+bool make_plan(Plan& pl, int nwc, int xs, int meta) {
     pl.nwc = nwc;
     pl.xs_bytes = (xs + 127) & ~127;
     pl.meta_bytes = (meta + 127) & ~127;
-    pl.slot_bytes = std::max(128, (slot + 127) & ~127);
     const int fixed = kCtrlBytes + pl.xs_bytes + 2 * pl.meta_bytes;
-    const int ring = g.max_smem - fixed;
-    if (ring <= 0) return false;
-    int n = ring / pl.slot_bytes;
-    if (g.opt_nslots > 0) n = std::min(n, g.opt_nslots);
-    n = std::min(n, kMaxSlots);
-    if (n < 4) return false;          // a task takes up to 4 slots
-    pl.nslots = n;
-    pl.smem = (size_t)fixed + (size_t)n * pl.slot_bytes;
+    const int ring = (g.max_smem - fixed) & ~127;
+    if (ring < 4 * 128) return false;
+    pl.ring_bytes = ring;
+    pl.smem = (size_t)fixed + (size_t)ring;
     return true;
 }
 
@@ -262,16 +257,22 @@ int op_min_chunk(const Op& op) {
 }
 // bytes of a whole warp-task (4 columns | 2 gate/up pairs | 4 rows)
 int op_task_chunks(const Op& op) { return op.kind == OP_FFN ? 2 : op.kind == OP_CLS ? op.rpt : 4; }
-int op_task_bytes(const Op& op) { return op_min_chunk(op) * op_task_chunks(op); }
-// cut the op's tasks into ring slots of `slot` bytes
-bool op_set_chunking(Op& op, int slot) {
+// Cut the op's tasks into ring slots: the largest piece of a task (whole, half, quarter) of at most kMaxChunk bytes is one
+// slot, and the ring holds as many of those as fit.  Ops with the same slot size share a ring epoch (interp_sm100.cuh).
+constexpr int kMaxChunk = 16384;
+bool op_set_chunking(Op& op, int ring_bytes) {
     const int per = op_task_chunks(op);             // chunks of minimum size per task
+    const int limit = g.opt_slot_bytes > 0 ? std::max(g.opt_slot_bytes, op_min_chunk(op)) : kMaxChunk;
     int cps = per;
-    while (cps >= 1 && cps * op_min_chunk(op) > slot) cps >>= 1;
-    if (cps < 1) return false;
+    while (cps > 1 && cps * op_min_chunk(op) > limit) cps >>= 1;
+    const int slot = (cps * op_min_chunk(op) + 127) & ~127;
+    int n = std::min(ring_bytes / slot, kMaxSlots);
+    if (g.opt_nslots > 0) n = std::min(n, g.opt_nslots);
     op.cps = cps;
     op.spt = per / cps;
-    return true;
+    op.slot_bytes = slot;
+    op.nslots = n;
+    return n >= op.spt && n >= 2;
 }
 // staging area: fp32 pairs (INT4 ops) or fp16 x (classifier), plus raw fp16 x and norm weights when RMSNorm is fused
 int op_xs_bytes(const Op& op) {
@@ -304,7 +305,7 @@ void launch_interp(const Plan& pl, const Op* d_ops, int nops, const Op* one, con
     InterpParams P;
     memset(&P, 0, sizeof P);
     P.ops = d_ops; P.nops = nops;
-    P.nwc = pl.nwc; P.nslots = pl.nslots; P.slot_bytes = pl.slot_bytes; P.meta_bytes = pl.meta_bytes; P.xs_bytes = pl.xs_bytes;
+    P.nwc = pl.nwc; P.ring_bytes = pl.ring_bytes; P.meta_bytes = pl.meta_bytes; P.xs_bytes = pl.xs_bytes;
     P.write_token = write_token;
     P.sync = g.sync; P.pPos = pPos;
     // Activation tags: consecutive launches over the same buffers must never share a tag.  Each plan advances its own base by
@@ -354,21 +355,19 @@ int default_nwc() { return g.opt_nwc > 0 ? std::min(g.opt_nwc, kMaxConsumerWarps
 // one op through the persistent kernel (operator API)
 void run_single(Op& op, const int* pPos) {
     Plan pl;
-    int grid = g.sm_count, xs = 0, meta = 0, slot = 128;
+    int grid = g.sm_count, xs = 0, meta = 0;
     if (op.kind <= OP_CLS) {
         grid = std::max(1, std::min(g.sm_count, op.ntasks));
         xs = op_xs_bytes(op);
         meta = op_meta_bytes(op, grid);
-        slot = g.opt_slot_bytes > 0 ? std::max(g.opt_slot_bytes, op_min_chunk(op)) : std::min(op_task_bytes(op), 16384);
-        slot = std::max(slot, op_min_chunk(op));
-        if (!op_set_chunking(op, slot)) unsupported();
     } else if (op.kind == OP_ATTN) {
         grid = std::min(g.sm_count, op.n_heads);
         xs = attn_scratch_bytes(op.head_size, op.max_seq);
     } else {
         grid = 1;
     }
-    if (!make_plan(pl, default_nwc(), xs, meta, slot)) unsupported();
+    if (!make_plan(pl, default_nwc(), xs, meta)) unsupported();
+    if (op.kind <= OP_CLS && !op_set_chunking(op, pl.ring_bytes)) unsupported();
     launch_interp(pl, nullptr, 1, &op, pPos, -1, false, grid);
 }
 
@@ -787,18 +786,16 @@ static NetPlan& get_net_plan(Config* p, RunState* s, TransformerWeights* w) {
     }
     if (!ok) return np;
 
-    int xs = attn_scratch_bytes(head_size, p->seq_len), meta = 0, slot = 0;
+    int xs = attn_scratch_bytes(head_size, p->seq_len), meta = 0;
     for (auto& op : ops) {
         if (op.kind > OP_CLS) continue;
         xs = std::max(xs, op_xs_bytes(op));
         meta = std::max(meta, op_meta_bytes(op, g.sm_count));
-        slot = std::max(slot, op_min_chunk(op));
     }
-    if (g.opt_slot_bytes > 0) slot = std::max(slot, g.opt_slot_bytes);
     const int nwc = default_nwc();
-    if (!make_plan(np.plan, nwc, xs, meta, slot)) return np;
+    if (!make_plan(np.plan, nwc, xs, meta)) return np;
     for (auto& op : ops)
-        if (op.kind <= OP_CLS && !op_set_chunking(op, np.plan.slot_bytes)) return np;
+        if (op.kind <= OP_CLS && !op_set_chunking(op, np.plan.ring_bytes)) return np;
     // the persistent kernel needs one co-resident CTA per SM
     int per_sm = 0;
     LQ4_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, interp_kernel, 32 * (nwc + 1), np.plan.smem));

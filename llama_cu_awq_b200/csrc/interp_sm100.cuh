@@ -62,6 +62,8 @@ struct Op {
     int T;                 // trips: ceil(K / 1024)  (OP_CLS: ceil(n / 256))
     int cps;               // columns (gate/up pairs, rows) per ring slot: 4, 2 or 1
     int spt;               // ring slots per warp-task
+    int slot_bytes;        // ring geometry of this op: bytes per slot (multiple of 128) ...
+    int nslots;            // ... and number of slots; consecutive ops with the same slot size share an epoch of the ring
     int rpt;               // OP_CLS: rows per warp-task (4, or 1 when a row is long enough to keep a warp busy)
     int au;                // CTA task ranges start on multiples of `au` tasks (16-byte alignment of the scale/zero copies)
     int ntasks;            // warp-tasks of the whole op (4 columns | 2 gate/up pairs | 4 rows each)
@@ -113,8 +115,7 @@ struct InterpParams {
     const Op* ops;         // device op table, or nullptr: use `one`
     int nops;
     int nwc;               // consumer warps per CTA (blockDim.x = 32 * (nwc + 1))
-    int nslots;            // ring slots
-    int slot_bytes;        // bytes per ring slot (multiple of 128)
+    int ring_bytes;        // bytes of the weight ring (cut into slots per op, see Op::slot_bytes)
     int meta_bytes;        // one scale/zero buffer (there are two)
     int xs_bytes;          // activation staging area (aliased with the attention scratch)
     int write_token;       // overrides Op::write_token of OP_ARGMAX when >= 0
@@ -130,13 +131,15 @@ struct InterpParams {
 };
 
 constexpr int kMaxConsumerWarps = 11;   // 12 warps = 3 per SM sub-partition: 168 registers per thread (a 4th warp on a sub-partition would cap them at 128)
-constexpr int kMaxSlots = 120;
+constexpr int kMaxSlots = 64;
 constexpr int kBarAll = 13;        // named barrier: all consumer warps
 constexpr int kCtrlBytes = 4096;   // mbarriers (first 2 KB) + reduction scratch (at 3 KB)
 constexpr int kRedOffset = 3072;
 constexpr unsigned kSpinLimit = 1u << 24;
 constexpr unsigned long long kWaitLimitNs = 5000000000ull;   // a wait longer than 5 s is a protocol bug (or a dead peer): trap
-constexpr int kLapOffset = 2048;   // per-slot release counters (up to 120 words)
+constexpr int kLapOffset = 2048;   // per-slot release counters (consumers), 64 words
+constexpr int kFillBaseOffset = 2304;   // per-slot fills before the current ring epoch (consumers), 64 words
+constexpr int kProdFillOffset = 3328;   // per-slot fills so far (producer lane only), 64 words
 constexpr int kOpOffset = 2560;    // the current op, copied from the table (512 bytes)
 // ------------------------------------------------------------------------------------------------
 // PTX: mbarrier, bulk copy, named barriers, coherent loads
@@ -353,18 +356,18 @@ __device__ __forceinline__ void gemv_locate(const Op& op, int c, int& seg, int& 
 }
 
 struct Smem {            // shared-memory map (shared-window addresses)
-    uint32_t bars;       // full[S], empty[S], mfull[2], mempty[2]
-    uint32_t laps;       // [S] releases of each slot so far (consumers only)
+    uint32_t bars;       // full[64], empty[64], mfull[2], mempty[2]
+    uint32_t laps;       // [64] releases of each slot so far (consumers only)
     uint32_t xs;         // activation staging / attention scratch
     uint32_t meta;       // [2][meta_bytes] scales and zero points of this CTA's columns, ping-pong per INT4 op
     int meta_bytes;
-    uint32_t ring;       // [S][slot_bytes]
-    int S, slot_bytes;
+    uint32_t ring;       // [S][slot_bytes] in the current epoch
+    int S, slot_bytes;   // geometry of the current ring epoch (0: none yet)
     __device__ __forceinline__ uint32_t full(int s) const { return bars + (uint32_t)s * 8; }
-    __device__ __forceinline__ uint32_t empty(int s) const { return bars + (uint32_t)(S + s) * 8; }
+    __device__ __forceinline__ uint32_t empty(int s) const { return bars + (uint32_t)(kMaxSlots + s) * 8; }
     __device__ __forceinline__ uint32_t slot(int s) const { return ring + (uint32_t)s * slot_bytes; }
-    __device__ __forceinline__ uint32_t mfull(int b) const { return bars + (uint32_t)(2 * S + b) * 8; }
-    __device__ __forceinline__ uint32_t mempty(int b) const { return bars + (uint32_t)(2 * S + 2 + b) * 8; }
+    __device__ __forceinline__ uint32_t mfull(int b) const { return bars + (uint32_t)(2 * kMaxSlots + b) * 8; }
+    __device__ __forceinline__ uint32_t mempty(int b) const { return bars + (uint32_t)(2 * kMaxSlots + 2 + b) * 8; }
     __device__ __forceinline__ uint32_t mbuf(int b) const { return meta + (uint32_t)b * meta_bytes; }
 };
 
@@ -377,8 +380,12 @@ struct Smem {            // shared-memory map (shared-window addresses)
 __device__ void producer_loop(const InterpParams& P, const Op* ops, const Smem& sm) {
     uint64_t policy;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-    int slot = 0;
-    uint32_t phase = 0;
+    // Ring epochs: consecutive ops with the same slot size share one; when the size changes the producer first waits for
+    // every slot to be released (the consumers are then inside their hand-over / staging, which hides the refill) and
+    // starts again at slot 0 with the new geometry.  pfill[i] = fills of slot i so far (parity of its barriers).
+    int slot = 0, S = 0, sbytes = 0;
+    const uint32_t pfill = sm.bars + kProdFillOffset;
+    auto ld_fill = [&](int i) { unsigned v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(pfill + i * 4) : "memory"); return v; };
     unsigned mcount = 0, issued = 0;
     for (int o = 0; o < P.nops; o++) {
         if (ops[o].kind > OP_CLS) continue;
@@ -386,6 +393,10 @@ __device__ void producer_loop(const InterpParams& P, const Op* ops, const Smem& 
         int t0, t1;
         cta_task_range(op, blockIdx.x, gridDim.x, t0, t1);
         const int cps = op.cps, spt = op.spt;
+        if (op.slot_bytes != sbytes) {
+            for (int i = 0; i < S; i++) mbar_wait(sm.empty(i), (ld_fill(i) & 1) ^ 1);     // drain: last fill of every slot released
+            S = op.nslots; sbytes = op.slot_bytes; slot = 0;
+        }
 
         if (op.kind != OP_CLS) {      // scales and zero points of the CTA's columns (layout: see stage_meta_layout)
             const int b = mcount & 1;
@@ -426,8 +437,9 @@ __device__ void producer_loop(const InterpParams& P, const Op* ops, const Smem& 
             int seg = 0, col = 0;
             if (op.kind == OP_GEMV) gemv_locate(op, task * 4, seg, col);
             for (int i = 0; i < spt; i++) {
-                mbar_wait(sm.empty(slot), phase ^ 1);
-                const uint32_t dst = sm.slot(slot), bar = sm.full(slot);
+                const unsigned pf = ld_fill(slot);
+                mbar_wait(sm.empty(slot), (pf & 1) ^ 1);
+                const uint32_t dst = sm.ring + (uint32_t)slot * sbytes, bar = sm.full(slot);
                 if (op.kind == OP_GEMV) {
                     const uint32_t bytes = (uint32_t)(cps * colb);
                     mbar_arrive_expect_tx(bar, bytes);
@@ -451,7 +463,8 @@ __device__ void producer_loop(const InterpParams& P, const Op* ops, const Smem& 
                         for (int r = 0; r < rows; r++) bulk_g2s(dst + r * colb, w + (size_t)r * op.row_stride, (uint32_t)colb, bar, policy);
                     }
                 }
-                if (++slot == sm.S) { slot = 0; phase ^= 1; }
+                asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(pfill + slot * 4), "r"(pf + 1) : "memory");
+                if (++slot == S) slot = 0;
                 issued++;
                 asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(sm.bars + 3584), "r"(issued) : "memory");
             }
@@ -714,25 +727,48 @@ __device__ __forceinline__ RingPos ring_pos(const Ctx& c, unsigned q) {
 __device__ __forceinline__ void ring_next(const Ctx& c, RingPos& r) {
     if (++r.slot == c.sm.S) { r.slot = 0; r.lap++; }
 }
-// Wait until chunk (slot, lap) has landed.  A parity wait cannot tell lap L from lap L-2, and a warp may be several
-// laps ahead of the ring (tasks are dealt round-robin), so first wait until the slot has been released `lap` times:
-// from then on the only phase of its full barrier that can still complete is this chunk's.
+// Wait until chunk (slot, lap of the current epoch) has landed.  A parity wait cannot tell one fill of a slot from the
+// one two fills later, and a warp may be several laps ahead of the ring (tasks are dealt round-robin), so first wait until
+// the slot has been released as often as it was filled before this chunk: from then on the only phase of its full barrier
+// that can still complete is this chunk's.  fill_base[slot] = fills before the current epoch.
+__device__ __forceinline__ unsigned ring_need(const Ctx& c, const RingPos& r) {
+    unsigned base;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(base) : "r"(c.sm.bars + kFillBaseOffset + r.slot * 4) : "memory");
+    return base + r.lap;
+}
 __device__ __forceinline__ void ring_wait(const Ctx& c, const RingPos& r) {
+    const unsigned need = ring_need(c, r);
     unsigned done;
     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(done) : "r"(c.sm.laps + r.slot * 4) : "memory");
-    if (done < r.lap) {
+    if (done < need) {
         const unsigned long long t0 = global_ns();
         do {
             asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(done) : "r"(c.sm.laps + r.slot * 4) : "memory");
             if (global_ns() - t0 > kWaitLimitNs) asm volatile("trap;");
-        } while (done < r.lap);
+        } while (done < need);
     }
-    mbar_wait(c.sm.full(r.slot), r.lap & 1);
+    mbar_wait(c.sm.full(r.slot), need & 1);
 }
 // lane 0 of the consuming warp, after the whole warp is done with the slot
 __device__ __forceinline__ void ring_release(const Ctx& c, const RingPos& r) {
-    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(c.sm.laps + r.slot * 4), "r"(r.lap + 1) : "memory");
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(c.sm.laps + r.slot * 4), "r"(ring_need(c, r) + 1) : "memory");
     mbar_arrive(c.sm.empty(r.slot));
+}
+// A new ring epoch starts when the op's slot size differs from the current one.  Called by all consumer threads between the
+// op's two opening named barriers: thread i folds the fills of slot i in the finished epoch into fill_base[i].
+__device__ __forceinline__ void ring_epoch(Ctx& c, int slot_bytes, int nslots) {
+    if (slot_bytes == c.sm.slot_bytes) return;
+    if (c.ctid < c.sm.S) {
+        const unsigned n = c.qbase, S = (unsigned)c.sm.S, i = (unsigned)c.ctid;
+        const unsigned fills = (n > i) ? (n - i + S - 1) / S : 0u;
+        const uint32_t a = c.sm.bars + kFillBaseOffset + i * 4;
+        unsigned v;
+        asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+        asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v + fills) : "memory");
+    }
+    c.qbase = 0;
+    c.sm.S = nslots;
+    c.sm.slot_bytes = slot_bytes;
 }
 
 __device__ void run_q4(Ctx& c, const Op& op, const NormRegs& nr) {
@@ -1289,8 +1325,8 @@ __global__ void __launch_bounds__(32 * (kMaxConsumerWarps + 1), 1) interp_kernel
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const Op* ops = (P.ops != nullptr) ? P.ops : &P.one;
     Smem sm;
-    sm.S = P.nslots;
-    sm.slot_bytes = P.slot_bytes;
+    sm.S = 0;
+    sm.slot_bytes = 0;
     sm.bars = smem_u32(smem);
     sm.laps = sm.bars + kLapOffset;
     sm.xs = sm.bars + kCtrlBytes;
@@ -1299,10 +1335,12 @@ __global__ void __launch_bounds__(32 * (kMaxConsumerWarps + 1), 1) interp_kernel
     sm.ring = sm.meta + 2 * P.meta_bytes;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < P.nslots; s++) {
+        for (int s = 0; s < kMaxSlots; s++) {
             mbar_init(sm.full(s), 1);
             mbar_init(sm.empty(s), 1);
             reinterpret_cast<volatile unsigned*>(smem + kLapOffset)[s] = 0u;
+            reinterpret_cast<volatile unsigned*>(smem + kFillBaseOffset)[s] = 0u;
+            reinterpret_cast<volatile unsigned*>(smem + kProdFillOffset)[s] = 0u;
         }
         for (int b = 0; b < 2; b++) { mbar_init(sm.mfull(b), 1); mbar_init(sm.mempty(b), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1331,6 +1369,7 @@ __global__ void __launch_bounds__(32 * (kMaxConsumerWarps + 1), 1) interp_kernel
         if (c.ctid < (int)(sizeof(Op) / 4))        // the op goes to shared memory: its fields are read many times per task
             reinterpret_cast<uint32_t*>(smem + kOpOffset)[c.ctid] = reinterpret_cast<const uint32_t*>(ops + o)[c.ctid];
         const int sync_before = ops[o].sync_before;
+        if (ops[o].kind <= OP_CLS) ring_epoch(c, ops[o].slot_bytes, ops[o].nslots);
         trace_mark(c, 5);                          // previous op: every warp of this CTA is done
         c.tr = (P.trace != nullptr && o == P.trace_op) ? P.trace + 2048 + blockIdx.x * 8 : nullptr;
         trace_mark(c, 0);                          // this CTA arrives at the op
