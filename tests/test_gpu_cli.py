@@ -66,3 +66,29 @@ def test_cli_usage_and_errors():
     assert r.returncode != 0 and "Usage:" in r.stderr and "-n <int>" in r.stderr
     r = subprocess.run([CLI, "model.bin", "-n"], capture_output=True, text=True)
     assert r.returncode != 0 and "Usage:" in r.stderr
+
+
+def test_cli_prompt_file_empty_prompt_and_step_clamp():
+    """-f reads the prompt from a file (and overrides -i with the reference's warning); no prompt at all starts from BOS alone;
+    -n larger than seq_len is clamped to seq_len (llama2_q4.cu:690)."""
+    import llama_cu_awq_b200 as E
+    lib = E.lib()
+    cfg = H.TINY
+    with tempfile.TemporaryDirectory() as d:
+        path, tok, pf = os.path.join(d, "m.bin"), os.path.join(d, "tok.bin"), os.path.join(d, "prompt.txt")
+        c = E.Config(**cfg)
+        assert lib.lq4_write_synth_model(path.encode(), C.byref(c), 5) == os.path.getsize(path)
+        assert lib.lq4_write_synth_tokenizer(tok.encode(), cfg["vocab_size"]) > 0
+        open(pf, "w").write("ab")
+        a, na = transcript(run(CLI, [path, "-z", tok, "-t", "0", "-n", "24", "-i", "ab"]))
+        out_f = run(CLI, [path, "-z", tok, "-t", "0", "-n", "24", "-i", "zz", "-f", pf])
+        assert "Warning: -f overrides -i" in out_f
+        b, nb = transcript(out_f)
+        assert na == nb == 23 and a[a.index("Done!"):] == b[b.index("Done!"):]
+        e, ne = transcript(run(CLI, [path, "-z", tok, "-t", "0", "-n", "16"]))
+        assert ne == 15
+        big, nbig = transcript(run(CLI, [path, "-z", tok, "-t", "0", "-n", "100000", "-i", "ab"]))
+        assert nbig == cfg["seq_len"] - 1
+        if os.path.exists(H.REF_BIN):
+            r, nr = transcript(run(H.REF_BIN, [path, "-z", tok, "-t", "0", "-n", "16"]))
+            assert nr == ne and r[r.index("Done!"):] == e[e.index("Done!"):]
