@@ -149,6 +149,9 @@ void lq4_enqueue_step(Transformer* t, Sampler* sampler, int seq_len, int gen_tok
 int lq4_step(Transformer* t, Sampler* sampler, int gen_token, lq4_half* logits_out, int* next_token_out);
 void lq4_reset(Transformer* t, const int* tokens, int n);   /* generate() init, llama2_q4.cu:461-463 */
 
+/* synchronises the engine stream, then copies device memory (e.g. RunState::logits_array, perplexity mode) to the host */
+int lq4_memcpy_to_host(void* dst, const void* src_device, size_t bytes);
+
 /* ---- tensor parallel, one process per GPU (new: the reference is single-GPU).  Column slices of every matrix per rank;
  * activations are broadcast by peer stores over NVLink (no collective call, no cross-GPU barrier); ids are bit-identical
  * to one GPU.  Order: lq4_tp_config -> lq4_build_transformer -> exchange lq4_tp_export handles -> lq4_tp_import each. ---- */

@@ -1132,6 +1132,15 @@ int lq4_generate_tokens(Transformer* t, Sampler* sampler, const int* prompt_toke
     return pos;
 }
 
+// device -> host copy for pure-host callers of the C ABI (the CLI's perplexity mode reads RunState::logits_array)
+int lq4_memcpy_to_host(void* dst, const void* src_device, size_t bytes) {
+    ensure_init();
+    cudaError_t e = cudaStreamSynchronize(g.stream);
+    if (e == cudaSuccess) e = cudaMemcpy(dst, src_device, bytes, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { set_err("lq4_memcpy_to_host", e); return 1; }
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------- tensor parallel (one process per GPU)
 // Rank / world of this process; call before lq4_build_transformer.  Every rank loads the whole .bin (a 7B model is 2 % of a
 // B200's memory) and streams only its column slices.

@@ -2,7 +2,7 @@
 //
 // Same invocation and the same stdout as the reference program (ankan-ban/llama_cu_awq llama2_q4.cu:604-720,
 // generate() :436-492): `llama2_q4_b200 <checkpoint> [-n int] [-i str] [-f file] [-t float] [-p float]
-// [-s int] [-z tokenizer] [-m generate|chat|perplexity] [-y sys] [-q dataset]`, flags strictly `-x value`
+// [-s int] [-z tokenizer] [-m generate|chat|perplexity] [-y sys] [-q dataset]` (all three modes), flags strictly `-x value`
 // pairs, defaults temperature 0.5 / topp 0.6 / tokenizer.bin, and the closing
 // `achieved tok/s: %f. Tokens: %d, seconds: %g` line.  Pure host C++ over the C ABI in
 // include/llama_q4_b200.h; nothing here touches CUDA directly.
@@ -15,11 +15,13 @@
 // on the device, so step t+1 is enqueued before the host has seen token t (LQ4_PIPELINE=0 restores the
 // reference's launch-wait-launch order).
 #include <ctype.h>
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
 
+#include <algorithm>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -174,6 +176,138 @@ void generate(Transformer* t, Tokenizer* tok, Sampler* sampler, const char* prom
     printf("\nachieved tok/s: %f. Tokens: %d, seconds: %g\n", timed_tokens / secs, timed_tokens, secs);
 }
 
+// ---------------------------------------------------------------------------- chat mode (llama2_q4.cu:494-601)
+void read_stdin(const char* guide, char* buffer, size_t bufsize) {
+    printf("%s", guide);
+    if (fgets(buffer, (int)bufsize, stdin) != NULL) {
+        size_t len = strlen(buffer);
+        if (len > 0 && buffer[len - 1] == '\n') buffer[len - 1] = '\0';
+    } else {
+        buffer[0] = '\0';
+    }
+}
+
+void chat(Transformer* t, Tokenizer* tok, Sampler* sampler, const char* cli_user_prompt, const char* cli_system_prompt, int steps) {
+    char system_prompt[512] = {0}, user_prompt[512] = {0};
+    std::string rendered;
+    std::vector<int> prompt_tokens;
+    int num_prompt_tokens = 0, user_idx = 0;
+    bool user_turn = true;
+    int next = 0, token = 0, pos = 0;
+    SharedData* sd = t->state.shared_data;
+    lq4_reset(t, &pos, 0);                       // device and host position to 0, no tokens yet
+    while (pos < steps) {
+        if (user_turn) {
+            if (pos == 0) {
+                if (cli_system_prompt == nullptr) read_stdin("Enter system prompt (optional): ", system_prompt, sizeof system_prompt);
+                else snprintf(system_prompt, sizeof system_prompt, "%s", cli_system_prompt);
+            }
+            if (pos == 0 && cli_user_prompt != nullptr) snprintf(user_prompt, sizeof user_prompt, "%s", cli_user_prompt);
+            else {
+                if (feof(stdin)) break;          // the reference would spin on an empty prompt; end the dialog instead
+                read_stdin("User: ", user_prompt, sizeof user_prompt);
+            }
+            if (pos == 0 && system_prompt[0] != '\0')
+                rendered = std::string("[INST] <<SYS>>\n") + system_prompt + "\n<</SYS>>\n\n" + user_prompt + " [/INST]";
+            else
+                rendered = std::string("[INST] ") + user_prompt + " [/INST]";
+            printf("\nRendered prompt: %s\n", rendered.c_str());
+            prompt_tokens = tok->encode(rendered.c_str(), true, false);
+            num_prompt_tokens = (int)prompt_tokens.size();
+            if (pos + num_prompt_tokens >= LQ4_MAX_SEQ_LEN) break;
+            user_idx = 0;
+            user_turn = false;
+            printf("Assistant: ");
+            lq4_stream_synchronize();
+            memcpy((void*)&sd->tokens[pos], prompt_tokens.data(), sizeof(int) * num_prompt_tokens);
+        }
+        lq4_stream_synchronize();
+        lq4_run_transformer(user_idx >= num_prompt_tokens - 1, &t->config, &t->state, &t->weights, 0, sampler);
+        user_idx++;
+        if (user_idx > 0) {
+            next = sd->tokens[pos];              // output of the previous iteration (or the prompt token at this position)
+            if (next == kEos) {
+                user_turn = true;
+                printf("\n");
+            } else if (user_idx > num_prompt_tokens) {
+                if (next >= 0 && next < t->config.vocab_size) tok->print_piece(token, next);
+                fflush(stdout);
+            }
+            token = next;
+        }
+        pos++;
+    }
+    printf("\n");
+    lq4_stream_synchronize();
+}
+
+// ---------------------------------------------------------------------------- perplexity mode (perplexity.h)
+float compute_perplexity(const int* tokens, float* logits, int num_tokens, int vocab_size) {   // perplexity.h:3-50
+    double sum = 0.0;
+    for (int i = 0; i < num_tokens; i++) {
+        float* x = logits + (size_t)i * vocab_size;
+        float max_val = x[0];
+        for (int v = 1; v < vocab_size; v++) if (x[v] > max_val) max_val = x[v];
+        float s = 0.0f;
+        for (int v = 0; v < vocab_size; v++) { x[v] = expf(x[v] - max_val); s += x[v]; }
+        for (int v = 0; v < vocab_size; v++) x[v] /= s;
+        sum += log((double)x[tokens[i]]);
+    }
+    return (float)exp(-sum / num_tokens);
+}
+
+float dataset_perplexity(const char* dataset, Transformer* t, Tokenizer* tok, Sampler* sampler) {   // perplexity.h:57-96
+    SharedData* sd = t->state.shared_data;
+    printf("\nTokenizing Dataset...");
+    std::vector<int> toks = tok->encode(dataset, false, false);
+    printf("done!\n");
+    printf("Found %d characters, %d tokens", (int)strlen(dataset), (int)toks.size());
+    int num = (int)toks.size();
+    if (num >= t->config.seq_len) { num = t->config.seq_len - 1; printf("\nTruncated to %d tokens", num); }
+    printf("\nRunning the network to get logits...");
+    int zero = 0;
+    lq4_reset(t, &zero, 0);
+    sd->tokens[0] = kBos;
+    memcpy((void*)&sd->tokens[1], toks.data(), sizeof(int) * (size_t)std::min<size_t>(toks.size(), LQ4_MAX_SEQ_LEN - 2));
+    for (int pos = 0; pos < num; pos++) {
+        lq4_run_transformer(0, &t->config, &t->state, &t->weights, 1, sampler);
+        lq4_stream_synchronize();
+    }
+    printf("done!\n");
+    printf("Computing perplexity...");
+    std::vector<float> logits((size_t)num * t->config.vocab_size);
+    if (num > 0 && lq4_memcpy_to_host(logits.data(), t->state.logits_array, logits.size() * sizeof(float)) != 0) exit(EXIT_FAILURE);
+    const float pplx = num > 0 ? compute_perplexity(&toks[0], logits.data(), num, t->config.vocab_size) : 1.0f;
+    printf("\nPerplexity computed on %d tokens: %f\n\n", num, pplx);
+    return pplx;
+}
+
+void parse_dataset_and_compute_perplexity(const char* path, Transformer* t, Tokenizer* tok, Sampler* sampler) {   // perplexity.h:99-139
+    FILE* fp = path ? fopen(path, "rb") : nullptr;
+    if (!fp) { printf("Couldn't open file %s\n", path ? path : "(null)"); exit(1); }
+    printf("\nLoading Dataset...");
+    fseek(fp, 0, SEEK_END);
+    const long bytes = ftell(fp);
+    fseek(fp, 0, SEEK_SET);
+    std::string data((size_t)bytes, '\0');
+    if (bytes > 0 && fread(&data[0], 1, (size_t)bytes, fp) != (size_t)bytes) { printf("error reading dataset\n"); exit(1); }
+    fclose(fp);
+    printf("done!\n");
+    int count = 0;
+    double product = 1;
+    size_t cur = 0;
+    const std::string sep = "<|endoftext|>";
+    for (;;) {
+        const size_t nxt = data.find(sep, cur);
+        const std::string seq = data.substr(cur, nxt == std::string::npos ? std::string::npos : nxt - cur);
+        product *= dataset_perplexity(seq.c_str(), t, tok, sampler);
+        count++;
+        if (nxt == std::string::npos) break;
+        cur = nxt + sep.size();
+    }
+    printf("\nGeomean perplexity on %d sequences: %f\n\n", count, pow(product, 1.0 / count));
+}
+
 }  // namespace
 
 int main(int argc, char* argv[]) {
@@ -182,6 +316,7 @@ int main(int argc, char* argv[]) {
     const char* dataset_path = nullptr;
     int steps = 0;
     char* prompt = nullptr;
+    const char* system_prompt = nullptr;
     float temperature = 0.5f, topp = 0.6f;   // llama2_q4.cu:632-633
     unsigned long long rng_seed = 0;
     const char* mode = "generate";
@@ -199,7 +334,7 @@ int main(int argc, char* argv[]) {
             case 'p': topp = (float)atof(argv[i + 1]); break;
             case 's': rng_seed = (unsigned long long)atoi(argv[i + 1]); break;
             case 'm': mode = argv[i + 1]; break;
-            case 'y': break;   // system prompt: chat mode only
+            case 'y': system_prompt = argv[i + 1]; break;
             case 'q': dataset_path = argv[i + 1]; break;
             case 'f': {
                 FILE* file = fopen(argv[i + 1], "r");
@@ -222,12 +357,7 @@ int main(int argc, char* argv[]) {
     if (temperature < 0.0f) temperature = 0.0f;
     if (topp < 0.0f || 1.0f < topp) topp = 0.9f;
     if (!perplexity && dataset_path) printf("Warning: dataset path is ignored in non-perplexity mode\n");
-    if (strcmp(mode, "generate") != 0) {
-        // chat and perplexity modes sit on the same hot path but are outside this engine's scope
-        if (strcmp(mode, "chat") != 0 && !perplexity) error_usage(argv);
-        fprintf(stderr, "mode '%s' is not built into llama2_q4_b200 (generate only)\n", mode);
-        return EXIT_FAILURE;
-    }
+    if (strcmp(mode, "generate") != 0 && strcmp(mode, "chat") != 0 && !perplexity) error_usage(argv);
 
     if (lq4_init(0) != 0) { fprintf(stderr, "%s\n", lq4_last_error()); return EXIT_FAILURE; }
     Transformer transformer;
@@ -238,7 +368,9 @@ int main(int argc, char* argv[]) {
     Sampler sampler;
     lq4_build_sampler(&sampler, transformer.config.vocab_size, temperature, topp, rng_seed);
 
-    generate(&transformer, &tokenizer, &sampler, prompt, steps);
+    if (perplexity) parse_dataset_and_compute_perplexity(dataset_path, &transformer, &tokenizer, &sampler);
+    else if (strcmp(mode, "generate") == 0) generate(&transformer, &tokenizer, &sampler, prompt, steps);
+    else chat(&transformer, &tokenizer, &sampler, prompt, system_prompt, steps);
 
     lq4_destroy_sampler(&sampler);
     lq4_free_transformer(&transformer);

@@ -92,3 +92,59 @@ def test_cli_prompt_file_empty_prompt_and_step_clamp():
         if os.path.exists(H.REF_BIN):
             r, nr = transcript(run(H.REF_BIN, [path, "-z", tok, "-t", "0", "-n", "16"]))
             assert nr == ne and r[r.index("Done!"):] == e[e.index("Done!"):]
+
+
+def _synth_files(d, cfg, seed):
+    import llama_cu_awq_b200 as E
+    lib = E.lib()
+    path, tok = os.path.join(d, "m.bin"), os.path.join(d, "tok.bin")
+    c = E.Config(**cfg)
+    assert lib.lq4_write_synth_model(path.encode(), C.byref(c), seed) == os.path.getsize(path)
+    assert lib.lq4_write_synth_tokenizer(tok.encode(), cfg["vocab_size"]) > 0
+    return path, tok
+
+
+def test_cli_perplexity_mode_matches_reference():
+    """`-m perplexity -q file` (perplexity.h:57-139): fp32 copies of every position's logits, host softmax, one
+    perplexity per `<|endoftext|>`-separated sequence and their geomean.  The logits are bit-exact, so the printed
+    numbers are too."""
+    with tempfile.TemporaryDirectory() as d:
+        path, tok = _synth_files(d, H.TINY, 21)
+        ds = os.path.join(d, "data.txt")
+        with open(ds, "w") as f:
+            f.write("the quick brown fox jumps over the lazy dog<|endoftext|>a second, shorter one<|endoftext|>" + "xyz " * 100)
+        args = [path, "-z", tok, "-m", "perplexity", "-q", ds]
+        mine = run(CLI, args)
+        vals = re.findall(r"Perplexity computed on (\d+) tokens: ([0-9.]+)", mine)
+        assert [int(v[0]) for v in vals] == [44, 22, 255], mine       # 1 dummy-prefix token + bytes; last one truncated to seq_len-1
+        assert "Truncated to 255 tokens" in mine and "Geomean perplexity on 3 sequences:" in mine
+        assert all(float(v[1]) > 1.0 for v in vals)
+        if not os.path.exists(H.REF_BIN):
+            pytest.skip("oracle/_ref/llama2_q4_ref not built")
+        ref = run(H.REF_BIN, args)
+        keep = lambda s: s[s.index("\nLoading Dataset..."):]
+        assert keep(mine) == keep(ref)
+
+
+def test_cli_chat_mode_matches_reference():
+    """`-m chat -i user -y system` (llama2_q4.cu:494-601): the rendered `[INST] <<SYS>>` prompt is fed token by token, then
+    the assistant's pieces are printed.  The synthetic classifier never emits EOS, so the dialog is one assistant turn
+    that runs to `-n`."""
+    with tempfile.TemporaryDirectory() as d:
+        path, tok = _synth_files(d, H.TINY, 22)
+        for extra in (["-y", "be brief"], ["-y", ""]):
+            args = [path, "-z", tok, "-m", "chat", "-t", "0", "-n", "120", "-i", "hello there"] + extra
+            r = subprocess.run([CLI] + args, capture_output=True, text=True, timeout=300, stdin=subprocess.DEVNULL)
+            assert r.returncode == 0, r.stderr[-500:]
+            mine = r.stdout
+            want = "[INST] <<SYS>>\nbe brief\n<</SYS>>\n\nhello there [/INST]" if extra[1] else "[INST] hello there [/INST]"
+            assert f"Rendered prompt: {want}\nAssistant: " in mine
+            body = mine.split("Assistant: ", 1)[1]
+            n_prompt = 2 + len(want)                                 # BOS + dummy prefix + one byte token per character
+            # byte tokens print as raw characters (unprintable ones are dropped), the rest as "[id]"
+            assert 20 <= len(re.findall(r"\[\d+\]|.", body)) <= 120 - n_prompt, body
+            if os.path.exists(H.REF_BIN):
+                rr = subprocess.run([H.REF_BIN] + args, capture_output=True, text=True, timeout=300, stdin=subprocess.DEVNULL)
+                assert rr.returncode == 0
+                cut = lambda s: s[s.index("\nRendered prompt:"):]
+                assert cut(mine) == cut(rr.stdout)
