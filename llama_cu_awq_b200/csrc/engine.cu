@@ -76,6 +76,7 @@ struct Engine {
     int tp_rank = 0, tp_world = 1;       // tensor parallel: one process per GPU, this one's rank
     int opt_trace = 0;      // record per-op timestamps of fused steps (development aid)
     int opt_trace_op = -1;  // op whose phases are recorded per CTA
+    int opt_nomath = 0;     // development aid (LQ4_NOMATH=1): data-path-only timing, results are garbage
     unsigned long long* trace = nullptr;
     int trace_n = 0;
     std::map<const void*, void*> arenas;   // Transformer* -> device arena (loader)
@@ -118,6 +119,7 @@ void ensure_init() {
     if ((env = getenv("LQ4_PDL"))) g.opt_pdl = atoi(env);
     if ((env = getenv("LQ4_FUSED"))) g.opt_fused = atoi(env);
     if ((env = getenv("LQ4_NWC"))) g.opt_nwc = atoi(env);
+    if ((env = getenv("LQ4_NOMATH"))) g.opt_nomath = atoi(env);
     if ((env = getenv("LQ4_NSLOTS"))) g.opt_nslots = atoi(env);
     if ((env = getenv("LQ4_SLOT_BYTES"))) g.opt_slot_bytes = atoi(env);
     LQ4_CHECK(cudaMalloc((void**)&g.sync, 2 * sizeof(unsigned)));
@@ -274,10 +276,9 @@ bool op_set_chunking(Op& op, int ring_bytes) {
     op.nslots = n;
     return n >= op.spt && n >= 2;
 }
-// staging area: fp32 pairs (INT4 ops) or fp16 x (classifier), plus raw fp16 x and norm weights when RMSNorm is fused
+// staging area: fp32 pairs (INT4 ops) or fp16 x (classifier, plus its parked norm weights when RMSNorm is fused)
 int op_xs_bytes(const Op& op) {
-    const int raw = op.norm_w != nullptr ? op.K * 4 : 0;
-    return (op.kind == OP_CLS ? ((op.K * 2 + 127) & ~127) : op.T * 4096) + raw;
+    return op.kind == OP_CLS ? ((op.K * 2 + 127) & ~127) * (op.norm_w != nullptr ? 2 : 1) : op.T * kTripBytes;
 }
 int op_meta_bytes(const Op& op, int grid) {
     if (op.kind == OP_CLS) return 0;
@@ -333,6 +334,7 @@ void launch_interp(const Plan& pl, const Op* d_ops, int nops, const Op* one, con
         P.trace_op = g.opt_trace_op;
         g.trace_n = nops + 1;
     }
+    P.nomath = g.opt_nomath;
     if (one) P.one = *one;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -681,6 +683,7 @@ static NetPlan& get_net_plan(Config* p, RunState* s, TransformerWeights* w) {
     const int kv_dim = (p->dim * p->n_kv_heads) / p->n_heads;
     const int kv_mul = p->n_heads / p->n_kv_heads;
     if ((head_size != 32 && head_size != 64 && head_size != 128) || p->seq_len > MAX_SEQ_LEN_SMEM_KERNEL) return np;
+    if (dim > 1024 * kNormMaxT || dim % 64) return np;      // fused RMSNorm staging (interp_sm100.cuh, stage_norm)
     // Tensor parallel (T ranks, one process per GPU): every matrix is split by output columns, rank r owning the r-th
     // contiguous slice (heads r*H/T.. for q|k|v and attention, hidden and dim slices for the FFN and the projections, vocabulary
     // rows for the classifier).  Each column is still computed entirely by one thread in the reference's order, so results are
@@ -792,7 +795,7 @@ static NetPlan& get_net_plan(Config* p, RunState* s, TransformerWeights* w) {
         xs = std::max(xs, op_xs_bytes(op));
         meta = std::max(meta, op_meta_bytes(op, g.sm_count));
     }
-    const int nwc = default_nwc();
+    const int nwc = std::max(default_nwc(), kNormThreads / 32);      // stage_norm needs 128 consumer threads
     if (!make_plan(np.plan, nwc, xs, meta)) return np;
     for (auto& op : ops)
         if (op.kind <= OP_CLS && !op_set_chunking(op, np.plan.ring_bytes)) return np;

@@ -127,6 +127,7 @@ struct InterpParams {
     const int* tokens;     // pinned-host token ring of the step (SharedData::tokens): read ONCE per launch, at its start
     unsigned long long* trace;   // optional [nops + 1] timestamps (ns): CTA 0 at the start of each op, and at the end
     int trace_op;                // op whose phases every CTA records at trace[2048 + cta * 8 + k]
+    int nomath;                  // development aid: consumers wait for and release their weights but skip the arithmetic (data-path-only timing)
     Op one;                // inline single op (operator API)
 };
 
@@ -264,6 +265,15 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
     return r;
 }
+__device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void sts_v2_u32(uint32_t addr, uint2 v) {
+    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t r;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
@@ -485,7 +495,8 @@ struct Ctx {
     int warp, lane, ctid;
     int pos;
     int token;                // tokens[pos], fetched over PCIe at the start of the launch
-    unsigned qbase;           // ring chunks of all ops before the current one (this CTA)
+    unsigned qbase;           // ring chunks of all ops before the current one in this ring epoch (this CTA)
+    unsigned qtotal;          // ... since the start of the launch (development aid)
     unsigned mcount;          // INT4 ops so far (scale/zero buffer = mcount & 1)
     int meta_pending;         // scale/zero buffer to hand back to the producer once every warp has left the op, or -1
     unsigned nsync;           // grid barriers taken so far
@@ -495,59 +506,17 @@ struct Ctx {
 __device__ __forceinline__ void cyc_mark(const Ctx& c, int k) {      // SM clock, warp 0 lane 0: sub-microsecond phases
     if (c.tr != nullptr && c.lane == 0 && c.warp == 0) (c.tr - blockIdx.x * 8 + 148 * 8 + blockIdx.x * 16)[k] = (unsigned long long)clock64();
 }
+// development aid: a raw value (not a clock) in slot k (8..15) of the CTA's cycle record
+__device__ __forceinline__ void val_mark(const Ctx& c, int k, unsigned long long v) {
+    if (c.tr != nullptr && c.lane == 0 && c.warp == 0) (c.tr - blockIdx.x * 8 + 148 * 8 + blockIdx.x * 16)[k] = v;
+}
+__device__ __forceinline__ unsigned producer_issued(const Ctx& c) {
+    unsigned v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(c.sm.bars + 3584) : "memory");
+    return v;
+}
 __device__ __forceinline__ void trace_mark(const Ctx& c, int k) {
     if (c.tr != nullptr && c.lane == 0 && (c.warp == 0 || k >= 8)) c.tr[k & 7] = global_ns();
-}
-
-// RMSNorm scale 1/sqrt(mean(x^2)+eps) in the reference's association (gpu_kernels.h:73-96): virtual
-// thread vt (of 1024) chains x[vt + 1024 i]^2, virtual warps are tree-summed, thread 0 adds the 32 warp
-// aggregates in order.  x is the raw fp16 vector already in shared memory.  All consumer threads call this;
-// returns the scale in every thread.
-__device__ float cta_rms_scale(Ctx& c, uint32_t xraw, int size) {
-    // A half-warp stands for one virtual warp: thread j holds the chains of virtual lanes 2j and 2j+1 (one 32-bit load per
-    // pair), so the first level of the cub tree is a local add and the other four are a butterfly over 16 threads.
-    const int ept = (size - 1) / 1024 + 1;
-    const int h = c.lane >> 4, j = c.lane & 15;
-    const uint32_t red = c.sm.bars + kRedOffset;
-    for (int vw = 2 * c.warp + h; vw < 32; vw += 2 * c.nwc) {      // both half-warps of a warp run the same number of passes
-        float sa = 0.0f, sb = 0.0f;
-        for (int i = 0; i < ept; i++) {
-            const int idx = vw * 32 + 2 * j + i * 1024;
-            if (idx + 1 < size) {
-                const uint32_t w = lds_u32(xraw + idx * 2);
-                const float a = h2f_bits(w & 0xFFFFu), b = h2f_bits(w >> 16);
-                sa = __fmaf_rn(a, a, sa);
-                sb = __fmaf_rn(b, b, sb);
-            } else if (idx < size) {
-                const float a = h2f_bits(lds_u16(xraw + idx * 2));
-                sa = __fmaf_rn(a, a, sa);
-            }
-        }
-        float v = sa + sb;
-        v = v + __shfl_xor_sync(0xffffffffu, v, 1);
-        v = v + __shfl_xor_sync(0xffffffffu, v, 2);
-        v = v + __shfl_xor_sync(0xffffffffu, v, 4);
-        v = v + __shfl_xor_sync(0xffffffffu, v, 8);
-        if (j == 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(red + vw * 4), "f"(v) : "memory");
-    }
-    named_bar(kBarAll, c.nthreads);
-    float tot;
-    {
-        float r[32];
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const uint4 t = lds_v4(red + q * 16);
-            r[4 * q] = __uint_as_float(t.x); r[4 * q + 1] = __uint_as_float(t.y); r[4 * q + 2] = __uint_as_float(t.z); r[4 * q + 3] = __uint_as_float(t.w);
-        }
-        tot = r[0];
-#pragma unroll
-        for (int w = 1; w < 32; w++) tot = tot + r[w];       // thread 0 of the reference adds the warp aggregates in order
-    }
-    tot = ((size & (size - 1)) == 0) ? __fmul_rn(tot, 1.0f / (float)size) : __fdiv_rn(tot, (float)size);   // exact either way
-    tot = tot + 1e-5f;
-    tot = __fdiv_rn(1.0f, __fsqrt_rn(tot));
-    // no trailing barrier: the scratch is next written in a later op, behind that op's opening barrier
-    return tot;
 }
 
 // fp16 bits of the (optionally normalised) activation element: half(x * (scale * w)), gpu_kernels.h:100-102
@@ -557,103 +526,256 @@ __device__ __forceinline__ uint32_t norm_h(uint32_t xh, uint32_t wh, float scale
     return f2h_bits(v);
 }
 __device__ __forceinline__ uint32_t word_of(const uint4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+__device__ __forceinline__ uint32_t pack_duo(const uint2& v) { return (v.x & 0xFFFFu) | (v.y << 16); }
+__device__ __forceinline__ bool tags_ok2(const uint2& v, uint32_t tag) { return ((v.x >> 16) == tag) & ((v.y >> 16) == tag); }
+__device__ __forceinline__ uint2 ld_vol_v2(const uint32_t* p) {
+    uint2 v;
+    asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_cg_u32(const void* p) {
+    uint32_t r;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// RMSNorm weights of the coming op, fetched while the grid barrier is pending (they do not depend on it)
-constexpr int kNormVecs = 3;
-struct NormRegs {
-    uint4 w[kNormVecs];
+// ------------------------------------------------------------------------------------------------
+// Activation staging.  Shared-memory layout read by the INT4 trips: thread (half-warp lane j) of a consumer warp owns
+// reference lanes A = 2j + sw and B = 2j + 1 - sw, sw = (j>>2)&1 (the swap keeps its two 16-byte weight loads bank-conflict
+// free).  Pair (trip t, j, i) = (x[t*1024 + A*32 + i], x[t*1024 + B*32 + i]) lives at byte t*kTripBytes + (i>>1)*kRowBytes +
+// j*16 + (i&1)*8: one 16-byte load per thread fetches two pairs and the 16 threads of a half-warp read 256 contiguous bytes.
+// The unit of staging is that 16-byte SLOT (t, i2, j): two consecutive elements of lane A and of lane B, i.e. two 8-byte
+// tagged vectors in, one 16-byte vector of pairs out.  Sixteen threads with consecutive i2 read one whole 128-byte line of
+// tagged words (polling by sectors multiplies the L2 requests of 148 CTAs); the row padding lets the same sixteen threads
+// write their slots to sixteen rows without bank conflicts.  All tagged vectors a thread needs are requested before the
+// first tag is examined, so a hand-over costs one trip to L2 once the data is there.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRowBytes = 272;      // 16 slots of 16 bytes + 16 bytes of padding: rows start one bank group apart
+constexpr int kTripBytes = 16 * kRowBytes;
+constexpr int kNormMaxT = 8;        // fused RMSNorm: K <= 8192 (the planner refuses larger)
+constexpr int kNormThreads = 256;   // 16 j x 16 slots of a lane pair
+#ifndef LQ4_NORM_CHUNK
+#define LQ4_NORM_CHUNK 4
+#endif
+#ifndef LQ4_PLAIN_CHUNK
+#define LQ4_PLAIN_CHUNK 8
+#endif
+constexpr int kNormChunk = LQ4_NORM_CHUNK;      // trips of a slot column whose tagged vectors are in flight together (2 vectors each)
+constexpr int kPollChunk = LQ4_PLAIN_CHUNK;     // slots of the plain staging in flight together (2 vectors each)
+
+struct SlotMap {       // slot -> (j, i2) and the element offsets of its two lanes inside a trip
+    int j, i2, offA, offB;
 };
-__device__ __forceinline__ void load_norm_regs(const Ctx& c, const Op& op, NormRegs& nr) {
+// Slot r (0..255) of a trip: i2 fastest, so a half-warp covers one lane pair (butterfly over i2 inside the warp)
+__device__ __forceinline__ SlotMap slot_map(int r) {
+    SlotMap m;
+    m.j = r >> 4;
+    m.i2 = r & 15;
+    const int sw = (m.j >> 2) & 1;
+    m.offA = (2 * m.j + sw) * 32 + m.i2 * 2;
+    m.offB = (2 * m.j + 1 - sw) * 32 + m.i2 * 2;
+    return m;
+}
+
+// Poll the tagged vectors at addr(i) (i in `want`) until every one carries `tag`; only the missing ones are requested again.
+template <int N, typename Addr>
+__device__ __forceinline__ void poll_vecs(uint2 (&v)[N], Addr addr, uint32_t want, uint32_t tag) {
 #pragma unroll
-    for (int r = 0; r < kNormVecs; r++) {
-        const int u = c.ctid + r * c.nthreads;
-        nr.w[r] = make_uint4(0, 0, 0, 0);
-        if (op.norm_w != nullptr && u * 8 < op.K) nr.w[r] = ldg_stream_v4(op.norm_w + u * 8);
+    for (int i = 0; i < N; i++)
+        if ((want >> i) & 1u) v[i] = ld_vol_v2(addr(i));
+    uint32_t pend = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++)
+        if (((want >> i) & 1u) && !tags_ok2(v[i], tag)) pend |= 1u << i;
+    if (pend) {
+        const unsigned long long t0 = global_ns();
+        do {
+            __nanosleep(40);        // idle CTAs poll for a long time (e.g. the 116 without a head during attention): stay off the L2
+#pragma unroll
+            for (int i = 0; i < N; i++)
+                if ((pend >> i) & 1u) v[i] = ld_vol_v2(addr(i));
+#pragma unroll
+            for (int i = 0; i < N; i++)
+                if (((pend >> i) & 1u) && tags_ok2(v[i], tag)) pend &= ~(1u << i);
+            if (global_ns() - t0 > kWaitLimitNs) asm volatile("trap;");
+        } while (pend);
     }
 }
 
-// Raw copies for a normalised op: x (one coherent 16-byte load per 8 elements: the only trip to L2 the
-// activations make) and the norm weights go to shared memory as fp16 at `xraw` / `xraw + K*2`; returns the
-// RMSNorm scale.  Ends with a named barrier.
-__device__ float stage_raw_and_scale(Ctx& c, const Op& op, const half* xin, uint32_t xraw, const NormRegs& nr) {
-    const int K = op.K;
-    const uint32_t wraw = xraw + K * 2;
-    int r = 0;
+// Fused RMSNorm + staging (rmsnorm_kernel, gpu_kernels.h:73-105).  The reference runs 1024 threads: thread vt chains
+// x[vt + 1024 i]^2, each warp is tree-summed (cub), thread 0 adds the 32 warp aggregates in order.  In trip coordinates
+// vt = lane*32 + i, i.e. reference lane L of the GEMV IS virtual warp L of the norm and element i its virtual lane.  A thread
+// owning slot i2 of lanes A and B over every trip holds two complete chains of each: tree level 1 is a local add, levels 2-5
+// a butterfly over the 16 threads of the lane pair.  256 threads do the whole vector; x is read from L2 once.  Until the scale is known a thread parks its raw elements (and, by asynchronous copy,
+// the norm weights) in the very slot it will overwrite with the result (private: no barrier, no bank conflicts).  Output: fp32
+// pairs (INT4 ops) or plain fp16 (classifier, whose weights are parked behind the vector).  Ends with a named barrier.
+template <bool PAIRS>
+__device__ __forceinline__ void norm_take(const Op& op, const SlotMap& m, uint32_t slot0, int t, uint32_t xa, uint32_t xb, float (&sa)[2], float (&sb)[2]) {
+    const float a0 = h2f_bits(xa & 0xFFFFu), a1 = h2f_bits(xa >> 16), b0 = h2f_bits(xb & 0xFFFFu), b1 = h2f_bits(xb >> 16);
+    sa[0] = __fmaf_rn(a0, a0, sa[0]); sa[1] = __fmaf_rn(a1, a1, sa[1]);
+    sb[0] = __fmaf_rn(b0, b0, sb[0]); sb[1] = __fmaf_rn(b1, b1, sb[1]);
+    if (PAIRS) {
+        sts_v2_u32(slot0 + t * kTripBytes, make_uint2(xa, xb));
+    } else {
+        sts_u32(slot0 + (t * 1024 + m.offA) * 2, xa); sts_u32(slot0 + (t * 1024 + m.offB) * 2, xb);
+    }
+    if (op.emb != nullptr && blockIdx.x == 0 && op.x_copy != nullptr) {      // layer 0: the embedding row becomes the residual stream
+        *reinterpret_cast<uint32_t*>(op.x_copy + t * 1024 + m.offA) = xa;
+        *reinterpret_cast<uint32_t*>(op.x_copy + t * 1024 + m.offB) = xb;
+    }
+}
+
+template <bool PAIRS>
+__device__ __forceinline__ void stage_norm(Ctx& c, const Op& op, const half* xin) {
+    const int K = op.K, T = (K + 1023) >> 10;
+    const uint32_t red = c.sm.bars + kRedOffset;
+    const bool worker = c.ctid < kNormThreads;
+    const SlotMap m = slot_map(c.ctid & 255);
+    const uint32_t slot0 = PAIRS ? c.sm.xs + m.i2 * kRowBytes + m.j * 16 : c.sm.xs;      // + t*4096: the thread's slot
+    const uint32_t wpark = c.sm.xs + ((K * 2 + 127) & ~127);                          // classifier: parked norm weights
+    if (worker) {
+        // the norm weights do not depend on the hand-over: asynchronous copies straight to their parking place
 #pragma unroll 1
-    for (int u = c.ctid; u * 8 < K; u += c.nthreads, r++) {
-        const uint4 xv = (op.xt != nullptr) ? poll8(op.xt + u * 8, c.tag_in) : ld_cg_v4(xin + u * 8);
-        uint4 wv;
-        if (r == 0) wv = nr.w[0]; else if (r == 1) wv = nr.w[1]; else if (r == 2) wv = nr.w[2]; else wv = ldg_stream_v4(op.norm_w + u * 8);
-        sts_v4_u32(xraw + u * 16, xv);
-        sts_v4_u32(wraw + u * 16, wv);
-        if (op.emb != nullptr && blockIdx.x == 0 && op.x_copy != nullptr) *reinterpret_cast<uint4*>(op.x_copy + u * 8) = xv;
+        for (int t = 0; t < T; t++) {
+            if (t * 1024 + m.offA < K) {          // K % 64 == 0: lanes A and B are live or dead together
+                cp_async4(PAIRS ? slot0 + t * kTripBytes + 8 : wpark + (t * 1024 + m.offA) * 2, op.norm_w + t * 1024 + m.offA);
+                cp_async4(PAIRS ? slot0 + t * kTripBytes + 12 : wpark + (t * 1024 + m.offB) * 2, op.norm_w + t * 1024 + m.offB);
+            }
+        }
+        float sa[2] = {0.0f, 0.0f}, sb[2] = {0.0f, 0.0f};
+        if (op.xt != nullptr) {
+#pragma unroll
+            for (int t0 = 0; t0 < kNormMaxT; t0 += kNormChunk) {
+                if (t0 < T) {
+                    uint2 v[2 * kNormChunk];
+                    uint32_t want = 0;
+#pragma unroll
+                    for (int q = 0; q < kNormChunk; q++)
+                        if (t0 + q < T && (t0 + q) * 1024 + m.offA < K) want |= 3u << (2 * q);
+                    const uint32_t* xt = op.xt;
+                    poll_vecs(v, [&](int i) { return xt + (t0 + (i >> 1)) * 1024 + ((i & 1) ? m.offB : m.offA); }, want, c.tag_in);
+#pragma unroll
+                    for (int q = 0; q < kNormChunk; q++)
+                        if ((want >> (2 * q)) & 1u) norm_take<PAIRS>(op, m, slot0, t0 + q, pack_duo(v[2 * q]), pack_duo(v[2 * q + 1]), sa, sb);
+                }
+            }
+        } else {      // plain fp16 input (embedding row of layer 0, stand-alone ops): nothing to wait for
+#pragma unroll 1
+            for (int t = 0; t < T; t++)
+                if (t * 1024 + m.offA < K)
+                    norm_take<PAIRS>(op, m, slot0, t, ld_cg_u32(xin + t * 1024 + m.offA), ld_cg_u32(xin + t * 1024 + m.offB), sa, sb);
+        }
+        float va = sa[0] + sa[1], vb = sb[0] + sb[1];
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) {
+            va = va + __shfl_xor_sync(0xffffffffu, va, d);
+            vb = vb + __shfl_xor_sync(0xffffffffu, vb, d);
+        }
+        if (m.i2 == 0) {
+            const int sw = (m.j >> 2) & 1;
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(red + (2 * m.j + sw) * 4), "f"(va) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(red + (2 * m.j + 1 - sw) * 4), "f"(vb) : "memory");
+        }
     }
     named_bar(kBarAll, c.nthreads);
-    cyc_mark(c, 1);                               // raw x and norm weights in shared memory
-    const float scale = cta_rms_scale(c, xraw, K);
-    cyc_mark(c, 2);                               // scale known
-    return scale;
+    cyc_mark(c, 1);                               // warp aggregates of x^2 in shared memory
+    if (worker) {
+        float tot;
+        {
+            float r[32];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const uint4 t = lds_v4(red + q * 16);
+                r[4 * q] = __uint_as_float(t.x); r[4 * q + 1] = __uint_as_float(t.y); r[4 * q + 2] = __uint_as_float(t.z); r[4 * q + 3] = __uint_as_float(t.w);
+            }
+            tot = r[0];
+#pragma unroll
+            for (int w = 1; w < 32; w++) tot = tot + r[w];       // thread 0 of the reference adds the warp aggregates in order
+        }
+        tot = ((K & (K - 1)) == 0) ? __fmul_rn(tot, 1.0f / (float)K) : __fdiv_rn(tot, (float)K);   // exact either way
+        tot = tot + 1e-5f;
+        const float scale = __fdiv_rn(1.0f, __fsqrt_rn(tot));
+        cyc_mark(c, 2);                           // scale known
+        cp_async_wait_all();                      // this thread's parked norm weights
+#pragma unroll 2
+        for (int t = 0; t < T; t++) {
+            if (t * 1024 + m.offA < K) {
+                uint32_t xa, xb, ga, gb;
+                if (PAIRS) {
+                    const uint4 r = lds_v4(slot0 + t * kTripBytes);
+                    xa = r.x; xb = r.y; ga = r.z; gb = r.w;
+                } else {
+                    xa = lds_u32(slot0 + (t * 1024 + m.offA) * 2); xb = lds_u32(slot0 + (t * 1024 + m.offB) * 2);
+                    ga = lds_u32(wpark + (t * 1024 + m.offA) * 2); gb = lds_u32(wpark + (t * 1024 + m.offB) * 2);
+                }
+                const uint32_t a0 = norm_h(xa & 0xFFFFu, ga & 0xFFFFu, scale, true), a1 = norm_h(xa >> 16, ga >> 16, scale, true);
+                const uint32_t b0 = norm_h(xb & 0xFFFFu, gb & 0xFFFFu, scale, true), b1 = norm_h(xb >> 16, gb >> 16, scale, true);
+                if (PAIRS) {
+                    sts_v4(slot0 + t * kTripBytes, h2f_bits(a0), h2f_bits(b0), h2f_bits(a1), h2f_bits(b1));
+                } else {
+                    sts_u32(slot0 + (t * 1024 + m.offA) * 2, a0 | (a1 << 16)); sts_u32(slot0 + (t * 1024 + m.offB) * 2, b0 | (b1 << 16));
+                }
+            }
+        }
+    }
+    named_bar(kBarAll, c.nthreads);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Activation staging for the INT4 ops: x (fp16, global) -> fp32 PAIRS in shared memory.
-// Thread (half-warp lane j) of a consumer warp owns reference lanes A = 2j + sw and B = 2j + 1 - sw, sw = (j>>2)&1
-// (the swap keeps its two 16-byte weight loads bank-conflict free).  Pair (trip t, j, i) = (x[t*1024 + A*32 + i],
-// x[t*1024 + B*32 + i]) lives at byte  t*4096 + (i>>1)*256 + j*16 + (i&1)*8, so that one 16-byte load per thread
-// fetches two pairs and the 16 threads of a half-warp read 256 contiguous bytes.
+// Staging for the INT4 ops: x (fp16: tagged words, plain global, or an embedding row) -> fp32 pairs in shared memory.
 // The caller has already passed a named barrier: nobody reads the staging area any more.
-// ------------------------------------------------------------------------------------------------
-__device__ void stage_x_pairs(Ctx& c, const Op& op, const NormRegs& nr) {
+__device__ void stage_x_pairs(Ctx& c, const Op& op) {
     const int K = op.K;
     const half* xin = op.x;
     if (op.emb != nullptr) {
         const int token = (op.tokens == c.P->tokens) ? c.token : op.tokens[c.pos];
         xin = op.emb + (size_t)token * K;
     }
-    const bool norm = (op.norm_w != nullptr);
-    const uint32_t xraw = c.sm.xs + op.T * 4096;      // raw fp16 x and norm weights sit behind the pairs
-    float scale = 1.0f;
-    if (norm) {
-        scale = stage_raw_and_scale(c, op, xin, xraw, nr);
-    } else if (op.emb != nullptr && blockIdx.x == 0 && op.x_copy != nullptr) {
-        for (int k = c.ctid; k < K; k += c.nthreads) op.x_copy[k] = xin[k];
+    if (op.norm_w != nullptr) {
+        stage_norm<true>(c, op, xin);
+        return;
     }
-    const int units = op.T * 64;      // (t, i8, j): 8 pairs each
-    constexpr int UB = 2;             // units in flight per thread (all loads first: one round trip to L2, not three)
+    if (op.emb != nullptr && blockIdx.x == 0 && op.x_copy != nullptr)
+        for (int k = c.ctid; k < K; k += c.nthreads) op.x_copy[k] = xin[k];
+    const int units = op.T * 256;     // slots, i2 fastest; the block size is a multiple of 16, so 16 consecutive threads always share a lane pair
+    const int nth = c.nthreads;
+    // first element of lane A (which = 0) or B (1) of slot u, and the slot's byte offset in the pair area
+    auto elem = [](int u, int which) {
+        const SlotMap m = slot_map(u & 255);
+        return (u >> 8) * 1024 + (which ? m.offB : m.offA);
+    };
+    auto slot_off = [](int u) {
+        const SlotMap m = slot_map(u & 255);
+        return (u >> 8) * kTripBytes + m.i2 * kRowBytes + m.j * 16;
+    };
+    if (op.xt != nullptr) {
 #pragma unroll 1
-    for (int ub = c.ctid; ub < units; ub += UB * c.nthreads) {
-        uint4 r0[UB], r1[UB], n0[UB], n1[UB];
+        for (int ub = c.ctid; ub < units; ub += kPollChunk * nth) {
+            uint2 v[2 * kPollChunk];
+            uint32_t want = 0;
+            const uint32_t* xt = op.xt;
 #pragma unroll
-        for (int v = 0; v < UB; v++) {
-            const int u = ub + v * c.nthreads;
-            const int t = u >> 6, i8 = (u >> 4) & 3, j = u & 15, sw = (j >> 2) & 1;
-            const int k0 = t * 1024 + (2 * j + sw) * 32 + i8 * 8, k1 = t * 1024 + (2 * j + 1 - sw) * 32 + i8 * 8;
-            r0[v] = r1[v] = n0[v] = n1[v] = make_uint4(0, 0, 0, 0);
-            if (u < units && k0 < K) {        // K % 64 == 0: both lanes of a thread are live or dead together
-                if (norm) {
-                    r0[v] = lds_v4(xraw + k0 * 2); r1[v] = lds_v4(xraw + k1 * 2);
-                    n0[v] = lds_v4(xraw + K * 2 + k0 * 2); n1[v] = lds_v4(xraw + K * 2 + k1 * 2);
-                } else if (op.xt != nullptr) {
-                    r0[v] = poll8(op.xt + k0, c.tag_in); r1[v] = poll8(op.xt + k1, c.tag_in);
-                } else {
-                    r0[v] = ld_cg_v4(xin + k0); r1[v] = ld_cg_v4(xin + k1);
+            for (int q = 0; q < kPollChunk; q++)
+                if (ub + q * nth < units && elem(ub + q * nth, 0) < K) want |= 3u << (2 * q);      // K % 64 == 0: both lanes are live or dead together
+            poll_vecs(v, [&](int i) { return xt + elem(ub + (i >> 1) * nth, i & 1); }, want, c.tag_in);
+#pragma unroll
+            for (int q = 0; q < kPollChunk; q++) {
+                if ((want >> (2 * q)) & 1u) {
+                    const int u = ub + q * nth;
+                    const uint32_t a = pack_duo(v[2 * q]), b = pack_duo(v[2 * q + 1]);
+                    sts_v4(c.sm.xs + slot_off(u), h2f_bits(a & 0xFFFFu), h2f_bits(b & 0xFFFFu), h2f_bits(a >> 16), h2f_bits(b >> 16));
                 }
             }
         }
-#pragma unroll
-        for (int v = 0; v < UB; v++) {
-            const int u = ub + v * c.nthreads;
-            const int t = u >> 6, i8 = (u >> 4) & 3, j = u & 15, sw = (j >> 2) & 1;
-            const int k0 = t * 1024 + (2 * j + sw) * 32 + i8 * 8;
-            if (u < units && k0 < K) {
-                const uint32_t dst = c.sm.xs + t * 4096 + (i8 * 4) * 256 + j * 16;
-#pragma unroll
-                for (int q = 0; q < 4; q++) {      // word q holds elements 2q, 2q+1
-                    const uint32_t a = word_of(r0[v], q), b = word_of(r1[v], q), na = word_of(n0[v], q), nb = word_of(n1[v], q);
-                    const float a0 = h2f_bits(norm_h(a & 0xFFFFu, na & 0xFFFFu, scale, norm)), a1 = h2f_bits(norm_h(a >> 16, na >> 16, scale, norm));
-                    const float b0 = h2f_bits(norm_h(b & 0xFFFFu, nb & 0xFFFFu, scale, norm)), b1 = h2f_bits(norm_h(b >> 16, nb >> 16, scale, norm));
-                    sts_v4(dst + q * 256, a0, b0, a1, b1);
-                }
+    } else {
+#pragma unroll 1
+        for (int u = c.ctid; u < units; u += nth) {
+            if (elem(u, 0) < K) {
+                const uint32_t a = ld_cg_u32(xin + elem(u, 0)), b = ld_cg_u32(xin + elem(u, 1));
+                sts_v4(c.sm.xs + slot_off(u), h2f_bits(a & 0xFFFFu), h2f_bits(b & 0xFFFFu), h2f_bits(a >> 16), h2f_bits(b >> 16));
             }
         }
     }
@@ -691,7 +813,7 @@ __device__ __forceinline__ void q4_trip2(unsigned long long& acc0, unsigned long
 #pragma unroll
         for (int e2 = 0; e2 < 4; e2++) {
             unsigned long long xp0, xp1;
-            lds_v2_b64(xaddr + (qi * 4 + e2) * 256, xp0, xp1);
+            lds_v2_b64(xaddr + (qi * 4 + e2) * kRowBytes, xp0, xp1);
             ffma2_pk(acc0, da0[2 * e2], db0[2 * e2], xp0);
             ffma2_pk(acc1, da1[2 * e2], db1[2 * e2], xp0);
             ffma2_pk(acc0, da0[2 * e2 + 1], db0[2 * e2 + 1], xp1);
@@ -771,23 +893,29 @@ __device__ __forceinline__ void ring_epoch(Ctx& c, int slot_bytes, int nslots) {
     c.sm.slot_bytes = slot_bytes;
 }
 
-__device__ void run_q4(Ctx& c, const Op& op, const NormRegs& nr) {
+__device__ void run_q4(Ctx& c, const Op& op) {
     int t0, t1;
     cta_task_range(op, blockIdx.x, gridDim.x, t0, t1);
-    stage_x_pairs(c, op, nr);
+    // everything that does not depend on the activations first: the hand-over below is where this warp waits anyway
     const int mb = c.mcount & 1;
     const uint32_t meta = c.sm.mbuf(mb);
-    trace_mark(c, 2);                                    // activations staged
-    cyc_mark(c, 3);
-
-    mbar_wait(c.sm.mfull(mb), (c.mcount >> 1) & 1);      // scales / zero points of this op have landed
-    cyc_mark(c, 4);
     const int K = op.K, T = op.T, G = q4_groups(K), zh = q4_zh(K), colb = q4_col_bytes(K);
     const int cps = op.cps, spt = op.spt, csh = (cps == 4) ? 2 : (cps == 2) ? 1 : 0;
     const bool dual = (op.kind == OP_FFN);
     const int h = c.lane >> 4, j = c.lane & 15, sw = (j >> 2) & 1;
     const int nseg = op.nseg, ncols0 = op.seg[0].ncols, ncols1 = op.seg[1].ncols;     // read once, not once per task
     RingPos rp = ring_pos(c, c.qbase + (unsigned)c.warp * spt);                        // this warp's first task
+    stage_x_pairs(c, op);
+    trace_mark(c, 2);                                    // activations staged
+    cyc_mark(c, 3);
+    if (c.tr != nullptr) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        val_mark(c, 8, producer_issued(c)); val_mark(c, 10, c.qtotal); val_mark(c, 11, smid);
+    }
+
+    mbar_wait(c.sm.mfull(mb), (c.mcount >> 1) & 1);      // scales / zero points of this op have landed
+    cyc_mark(c, 4);
 #pragma unroll 1
     for (int task = t0 + c.warp; task < t1; task += c.nwc) {
         // ---- my two columns: where their weights, scales and zeros are ----
@@ -823,16 +951,16 @@ __device__ void run_q4(Ctx& c, const Op& op, const NormRegs& nr) {
             if ((i1 >> csh) != (i0 >> csh)) ring_next(c, r);
             w1 = c.sm.slot(r.slot) + (i1 & (cps - 1)) * colb;
         }
-        if (task == t0) { trace_mark(c, 3); cyc_mark(c, 5); }   // warp 0: first task's weights are in shared memory
+        if (task == t0) { trace_mark(c, 3); cyc_mark(c, 5); if (c.tr != nullptr) val_mark(c, 9, producer_issued(c)); }   // warp 0: first task's weights are in shared memory
         w0 += j * 32 + sw * 16;
         w1 += j * 32 + sw * 16;
         unsigned long long acc0 = 0ull, acc1 = 0ull;
         const int tlive = (K - j * 64 + 1023) >> 10;      // trips in which this thread's lanes hold data
 #pragma unroll 1
         for (int t = 0; t < T; t++) {
-            if (t < tlive) {
+            if (t < tlive && !c.P->nomath) {
                 const ColMeta m0 = col_meta(scol0, zcol0, t, j), m1 = col_meta(scol1, zcol1, t, j);
-                q4_trip2(acc0, acc1, c.sm.xs + t * 4096 + j * 16, w0 + t * 512, w1 + t * 512, m0, m1);
+                q4_trip2(acc0, acc1, c.sm.xs + t * kTripBytes + j * 16, w0 + t * 512, w1 + t * 512, m0, m1);
             }
         }
         __syncwarp();
@@ -885,6 +1013,7 @@ __device__ void run_q4(Ctx& c, const Op& op, const NormRegs& nr) {
     }
     trace_mark(c, 4);                                    // warp 0 has finished its tasks
     c.qbase += (unsigned)(t1 - t0) * spt;
+    c.qtotal += (unsigned)(t1 - t0) * spt;
     c.meta_pending = mb;
     c.mcount++;
 }
@@ -893,35 +1022,19 @@ __device__ void run_q4(Ctx& c, const Op& op, const NormRegs& nr) {
 // fp16 classifier consumer (mat_vec_kernel, gpu_kernels.h:109-139).  Reference lane L chains
 // k = (trip*32 + L)*8 + el over trips of 256 k; one thread is one reference lane of four rows.
 // ------------------------------------------------------------------------------------------------
-__device__ void run_cls(Ctx& c, const Op& op, const NormRegs& nr) {
+__device__ void run_cls(Ctx& c, const Op& op) {
     const int n = op.K, T = op.T, lane = c.lane, cps = op.cps, spt = op.spt;
     // ---- stage x as fp16 (through the fused RMSNorm); the caller has passed a named barrier ----
-    {
-        const bool norm = (op.norm_w != nullptr);
-        const uint32_t xraw = c.sm.xs + ((n * 2 + 127) & ~127);
-        float scale = 1.0f;
-        if (norm) scale = stage_raw_and_scale(c, op, op.x, xraw, nr);
+    if (op.norm_w != nullptr) {
+        stage_norm<false>(c, op, op.x);
+    } else {
 #pragma unroll 1
         for (int u = c.ctid; u * 8 < n; u += c.nthreads) {
-            uint4 xv;
-            if (norm) {
-                xv = lds_v4(xraw + u * 16);
-                const uint4 wv = lds_v4(xraw + n * 2 + u * 16);
-                uint32_t* xw = &xv.x;
-                const uint32_t* ww = &wv.x;
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const uint32_t lo = norm_h(xw[q] & 0xFFFFu, ww[q] & 0xFFFFu, scale, true);
-                    const uint32_t hi = norm_h(xw[q] >> 16, ww[q] >> 16, scale, true);
-                    xw[q] = lo | (hi << 16);
-                }
-            } else {
-                xv = (op.xt != nullptr) ? poll8(op.xt + u * 8, c.tag_in) : ld_cg_v4(op.x + u * 8);
-            }
+            const uint4 xv = (op.xt != nullptr) ? poll8(op.xt + u * 8, c.tag_in) : ld_cg_v4(op.x + u * 8);
             sts_v4_u32(c.sm.xs + u * 16, xv);
         }
+        named_bar(kBarAll, c.nthreads);
     }
-    named_bar(kBarAll, c.nthreads);
 
     int t0, t1;
     cta_task_range(op, blockIdx.x, gridDim.x, t0, t1);
@@ -944,7 +1057,7 @@ __device__ void run_cls(Ctx& c, const Op& op, const NormRegs& nr) {
         float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         for (int t = 0; t < T; t++) {
             const int jx = (t * 32 + lane) * 8;
-            if (jx < n) {
+            if (jx < n && !c.P->nomath) {
                 const uint4 xv = lds_v4(c.sm.xs + jx * 2);
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
@@ -972,6 +1085,7 @@ __device__ void run_cls(Ctx& c, const Op& op, const NormRegs& nr) {
         }
     }
     c.qbase += (unsigned)(t1 - t0) * spt;
+    c.qtotal += (unsigned)(t1 - t0) * spt;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1360,7 +1474,7 @@ __global__ void __launch_bounds__(32 * (kMaxConsumerWarps + 1), 1) interp_kernel
     c.nwc = P.nwc; c.nthreads = P.nwc * 32; c.warp = warp; c.lane = lane; c.ctid = threadIdx.x;
     c.pos = (P.pPos != nullptr) ? *P.pPos : 0;
     c.token = (P.tokens != nullptr) ? P.tokens[c.pos] : 0;
-    c.qbase = 0; c.mcount = 0; c.meta_pending = -1; c.nsync = 0; c.tr = nullptr; c.tag_in = c.tag_out = 0;
+    c.qbase = 0; c.qtotal = 0; c.mcount = 0; c.meta_pending = -1; c.nsync = 0; c.tr = nullptr; c.tag_in = c.tag_out = 0;
 
     const Op& op = *reinterpret_cast<const Op*>(smem + kOpOffset);
     for (int o = 0; o < P.nops; o++) {
@@ -1381,8 +1495,6 @@ __global__ void __launch_bounds__(32 * (kMaxConsumerWarps + 1), 1) interp_kernel
         c.meta_pending = -1;
         c.tag_out = ((P.seq_base + (unsigned)o + 1u) & 0x7FFFu) | 0x8000u;     // never 0: a zeroed buffer is never "fresh"
         c.tag_in = ((P.seq_base + (unsigned)o) & 0x7FFFu) | 0x8000u;           // the previous op's
-        NormRegs nr;
-        load_norm_regs(c, ops[o], nr);             // in flight while the grid barrier completes
         const bool attn_pref = (ops[o].kind == OP_ATTN);
         if (attn_pref) attn_prefetch(c, ops[o]);   // K rows of earlier positions do not depend on this launch at all
         if (sync_before) {
@@ -1395,8 +1507,8 @@ __global__ void __launch_bounds__(32 * (kMaxConsumerWarps + 1), 1) interp_kernel
         cyc_mark(c, 0);
         switch (op.kind) {
             case OP_GEMV:
-            case OP_FFN: run_q4(c, op, nr); break;
-            case OP_CLS: run_cls(c, op, nr); break;
+            case OP_FFN: run_q4(c, op); break;
+            case OP_CLS: run_cls(c, op); break;
             case OP_ATTN: run_attn(c, op, attn_pref); break;
             case OP_ARGMAX: run_argmax(c, op, (P.write_token >= 0) ? P.write_token : op.write_token); break;
             default: break;

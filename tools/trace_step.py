@@ -57,9 +57,22 @@ print(f"op {trace_op} ({names[kinds[trace_op] // 100000]} K={kinds[trace_op] % 1
 for k, name in enumerate(["arrive(prev done)", "barrier passed", "x staged", "first weights", "warp0 done", "all warps done", "warp0 task 1 done", "warp0 task 2 done"]):
     print(f"  {name:18s} {rel[:, k].min():8.2f} {np.median(rel[:, k]):8.2f} {rel[:, k].max():8.2f}")
 
+smid = [int(ts[2048 + 148 * 8 + b * 16 + 11]) for b in range(nb)]
+late = [b for b in range(nb) if rel[b, 2] > np.median(rel[:, 2]) + 0.7]
+print(f"  CTAs with x staged > median + 0.7 us: {len(late)}: " + ", ".join(f"cta{b}/sm{smid[b]}:{rel[b, 2]:.2f}" for b in late))
+for k, name in ((0, "arrive"), (2, "x staged"), (5, "all warps done")):
+    order = np.argsort(-rel[:, k])[:8]
+    print(f"  slowest CTAs at '{name}': " + ", ".join(f"{int(b)}:{rel[b, k]:.2f}" for b in order))
+print("  duration x staged -> all warps done [min/median/max]: %.2f %.2f %.2f; slowest: %s" % (
+    (rel[:, 5] - rel[:, 2]).min(), np.median(rel[:, 5] - rel[:, 2]), (rel[:, 5] - rel[:, 2]).max(),
+    ", ".join(f"{int(b)}:{rel[b, 5] - rel[b, 2]:.2f}" for b in np.argsort(-(rel[:, 5] - rel[:, 2]))[:8])))
 cy = np.array([[ts[2048 + 148 * 8 + b * 16 + k] for k in range(8)] for b in range(nb)], dtype=np.float64)
 names_c = ["barrier passed", "raw x staged", "rms scale known", "pairs staged", "meta landed", "first weights", "first task done", "(arrive)"]
 print("  SM-clock phases of warp 0, cycles since 'barrier passed' [median over CTAs] (1965 cycles = 1 us):")
 for k in range(1, 7):
     print(f"    {names_c[k]:18s} {np.median(cy[:, k] - cy[:, 0]):9.0f}")
 print(f"    arrive -> passed   {np.median(cy[:, 0] - cy[:, 7]):9.0f}")
+ex = np.array([[ts[2048 + 148 * 8 + b * 16 + k] for k in range(8, 11)] for b in range(nb)], dtype=np.float64)
+ahead0, ahead1 = ex[:, 0] - ex[:, 2], ex[:, 1] - ex[:, 2]
+print(f"  ring chunks the producer was ahead of this op's first chunk [min/median/max over CTAs]: when x was staged {ahead0.min():.0f}/{np.median(ahead0):.0f}/{ahead0.max():.0f}, "
+      f"when warp 0 got its first weights {ahead1.min():.0f}/{np.median(ahead1):.0f}/{ahead1.max():.0f}")
