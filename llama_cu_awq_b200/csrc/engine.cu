@@ -40,7 +40,7 @@ struct RopeKey {
 
 // launch geometry of the persistent kernel (shared-memory map of interp_sm100.cuh)
 struct Plan {
-    int nwc = 0, ring_bytes = 0, meta_bytes = 0, xs_bytes = 0;
+    int nwc = 0, ring_bytes = 0, meta_bytes = 0, meta1_bytes = 0, xs_bytes = 0;
     size_t smem = 0;
 };
 
@@ -204,12 +204,14 @@ long time_in_ms() {   // llama2_q4.cu:400-405
 int attn_scratch_bytes(int head_size, int max_seq) { return attn_fixed_bytes(head_size, max_seq) + 2 * attn_buf_bytes(head_size); }
 
 // Shared-memory plan for `nwc` consumer warps: a staging area of `xs` bytes (activations / attention scratch),
-// `meta` bytes of scales / zero points and as many ring slots of `slot` bytes as fit.
-bool make_plan(Plan& pl, int nwc, int xs, int meta) {
+// two buffers of scales / zero points (`meta` bytes for the even INT4 ops of the table, `meta1` for the odd ones: they are
+// used alternately) and as many ring slots of `slot` bytes as fit.
+bool make_plan(Plan& pl, int nwc, int xs, int meta, int meta1) {
     pl.nwc = nwc;
     pl.xs_bytes = (xs + 127) & ~127;
     pl.meta_bytes = (meta + 127) & ~127;
-    const int fixed = kCtrlBytes + pl.xs_bytes + 2 * pl.meta_bytes;
+    pl.meta1_bytes = (meta1 + 127) & ~127;
+    const int fixed = kCtrlBytes + pl.xs_bytes + pl.meta_bytes + pl.meta1_bytes;
     const int ring = (g.max_smem - fixed) & ~127;
     if (ring < 4 * 128) return false;
     pl.ring_bytes = ring;
@@ -306,7 +308,7 @@ void launch_interp(const Plan& pl, const Op* d_ops, int nops, const Op* one, con
     InterpParams P;
     memset(&P, 0, sizeof P);
     P.ops = d_ops; P.nops = nops;
-    P.nwc = pl.nwc; P.ring_bytes = pl.ring_bytes; P.meta_bytes = pl.meta_bytes; P.xs_bytes = pl.xs_bytes;
+    P.nwc = pl.nwc; P.ring_bytes = pl.ring_bytes; P.meta_bytes = pl.meta_bytes; P.meta1_bytes = pl.meta1_bytes; P.xs_bytes = pl.xs_bytes;
     P.write_token = write_token;
     P.sync = g.sync; P.pPos = pPos;
     // Activation tags: consecutive launches over the same buffers must never share a tag.  Each plan advances its own base by
@@ -368,7 +370,7 @@ void run_single(Op& op, const int* pPos) {
     } else {
         grid = 1;
     }
-    if (!make_plan(pl, default_nwc(), xs, meta)) unsupported();
+    if (!make_plan(pl, default_nwc(), xs, meta, 0)) unsupported();      // a single op only ever uses buffer 0
     if (op.kind <= OP_CLS && !op_set_chunking(op, pl.ring_bytes)) unsupported();
     launch_interp(pl, nullptr, 1, &op, pPos, -1, false, grid);
 }
@@ -789,14 +791,16 @@ static NetPlan& get_net_plan(Config* p, RunState* s, TransformerWeights* w) {
     }
     if (!ok) return np;
 
-    int xs = attn_scratch_bytes(head_size, p->seq_len), meta = 0;
+    // scale/zero buffers alternate per INT4 op: q|k|v and gate/up land in buffer 0, o and down in buffer 1, so each is sized
+    // for its own ops only
+    int xs = attn_scratch_bytes(head_size, p->seq_len), meta[2] = {0, 0}, nq4 = 0;
     for (auto& op : ops) {
         if (op.kind > OP_CLS) continue;
         xs = std::max(xs, op_xs_bytes(op));
-        meta = std::max(meta, op_meta_bytes(op, g.sm_count));
+        if (op.kind != OP_CLS) { meta[nq4 & 1] = std::max(meta[nq4 & 1], op_meta_bytes(op, g.sm_count)); nq4++; }
     }
     const int nwc = std::max(default_nwc(), kNormThreads / 32);      // stage_norm needs 128 consumer threads
-    if (!make_plan(np.plan, nwc, xs, meta)) return np;
+    if (!make_plan(np.plan, nwc, xs, meta[0], meta[1])) return np;
     for (auto& op : ops)
         if (op.kind <= OP_CLS && !op_set_chunking(op, np.plan.ring_bytes)) return np;
     // the persistent kernel needs one co-resident CTA per SM

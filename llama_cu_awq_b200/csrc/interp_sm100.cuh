@@ -116,7 +116,8 @@ struct InterpParams {
     int nops;
     int nwc;               // consumer warps per CTA (blockDim.x = 32 * (nwc + 1))
     int ring_bytes;        // bytes of the weight ring (cut into slots per op, see Op::slot_bytes)
-    int meta_bytes;        // one scale/zero buffer (there are two)
+    int meta_bytes;        // scale/zero buffer 0 (even INT4 ops of the table)
+    int meta1_bytes;       // scale/zero buffer 1 (odd INT4 ops)
     int xs_bytes;          // activation staging area (aliased with the attention scratch)
     int write_token;       // overrides Op::write_token of OP_ARGMAX when >= 0
     unsigned seq_base;     // launch counter * nops: makes the activation tags of this launch unique
@@ -369,7 +370,7 @@ struct Smem {            // shared-memory map (shared-window addresses)
     uint32_t bars;       // full[64], empty[64], mfull[2], mempty[2]
     uint32_t laps;       // [64] releases of each slot so far (consumers only)
     uint32_t xs;         // activation staging / attention scratch
-    uint32_t meta;       // [2][meta_bytes] scales and zero points of this CTA's columns, ping-pong per INT4 op
+    uint32_t meta;       // two buffers (meta_bytes, then meta1 bytes) of scales and zero points of this CTA's columns, ping-pong per INT4 op
     int meta_bytes;
     uint32_t ring;       // [S][slot_bytes] in the current epoch
     int S, slot_bytes;   // geometry of the current ring epoch (0: none yet)
@@ -1446,7 +1447,7 @@ __global__ void __launch_bounds__(32 * (kMaxConsumerWarps + 1), 1) interp_kernel
     sm.xs = sm.bars + kCtrlBytes;
     sm.meta = sm.xs + P.xs_bytes;
     sm.meta_bytes = P.meta_bytes;
-    sm.ring = sm.meta + 2 * P.meta_bytes;
+    sm.ring = sm.meta + P.meta_bytes + P.meta1_bytes;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kMaxSlots; s++) {
