@@ -90,7 +90,7 @@ class ClockSampler:
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -278,7 +278,6 @@ def main():
         ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
-    clk = clocks.stop()
     ms = max_over_ranks(ms, world)
     tokens_dev = [int(t.state.shared_data.contents.tokens[i]) for i in range(K + 1)]
 
@@ -291,6 +290,7 @@ def main():
     assert list(out)[1:n] == tokens_dev[1:n], "pipelined host API and raw enqueue disagree on token ids"
     if world > 1:
         e2e_val = (n - 1) / max_over_ranks(secs.value, world)
+    clk = clocks.stop()             # sampled across both timed regions (device-timed steps and the end-to-end call)
     units = 1 if tp else world        # tensor parallel: all ranks decode ONE stream; replicas: one stream each
 
     # ---- roofline ----
