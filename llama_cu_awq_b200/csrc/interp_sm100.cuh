@@ -1094,78 +1094,50 @@ __device__ void run_cls(Ctx& c, const Op& op) {
 // (RoPERotation_kernel :332-355, mat_vec_kernel_simple :142-168, softmax_kernel :357-401,
 //  vec_mat_kernel :279-329).  The reference's 1024-thread reductions are replayed with virtual threads.
 //
-// K and V rows of earlier positions are staged through shared memory in tiles of kAttnTile rows with cooperative
-// 16-byte loads (one trip to L2 per tile instead of one per row); the first tile of both is fetched BEFORE the grid
-// barrier that precedes the op, since rows t < pos were written by earlier launches.
-// Scratch layout (floats unless noted): qs[hs] | krow[hs] | vrow[hs] | att[max_seq] | bufA (tile, fp16; later `part`) | bufB (tile, fp16)
+// K and V rows of earlier positions stream through shared memory in tiles of kAttnTile rows, four tile buffers deep, with
+// asynchronous 16-byte copies (cp.async: no registers, three tiles in flight while one is consumed, one named barrier per
+// tile); the first three K tiles are requested BEFORE the hand-over that precedes the op, since rows t < pos were written by
+// earlier launches.
+// Scratch layout (floats unless noted): qs[hs] | krow[hs] | vrow[hs] | att[max_seq] | 4 tile buffers (fp16; the first two later hold `part`)
 // ------------------------------------------------------------------------------------------------
-constexpr int kAttnTile = 64;
-__host__ __device__ __forceinline__ int attn_buf_bytes(int hs) {
-    const int tile = kAttnTile * hs * 2, part = 32 * hs * 4;
+constexpr int kAttnTile = 32;
+constexpr int kAttnAhead = 3;      // tiles requested ahead of the one being consumed (kAttnAhead + 1 buffers)
+__host__ __device__ __forceinline__ int attn_buf_bytes(int hs) {      // two tile buffers, or the 32 x hs fp32 partial sums of the PV tree
+    const int tile = 2 * kAttnTile * hs * 2, part = 32 * hs * 4;
     return ((tile > part ? tile : part) + 127) & ~127;
 }
 __host__ __device__ __forceinline__ int attn_fixed_bytes(int hs, int max_seq) { return ((3 * hs + ((max_seq + 3) & ~3)) * 4 + 127) & ~127; }
+__device__ __forceinline__ uint32_t attn_tile_buf(const Ctx& c, int hs, int max_seq, int ti) {
+    return c.sm.xs + attn_fixed_bytes(hs, max_seq) + (uint32_t)(ti & kAttnAhead) * (kAttnTile * hs * 2);
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// rows [row0, row0 + nrows) of one head (hs halfs each, kv_stride apart) -> shared memory, row-major
-// One batch of a tile copy: up to three 16-byte vectors per thread in flight (a 64 x 128 tile is one batch for 342+ threads).
-constexpr int kAttnVecs = 3;
-struct TileRegs {
-    uint4 v[kAttnVecs];
-};
-__device__ __forceinline__ void attn_tile_ld(const Ctx& c, TileRegs& t, const half* base, int kv_stride, int hs, int row0, int nrows, int first) {
+// Request tile ti (rows [ti*kAttnTile, ...) of one head: hs halfs each, kv_stride apart) into its buffer and close a copy group.
+// A tile past the end is an empty group, so that every caller's group count stays the same.
+__device__ __forceinline__ void attn_tile_async(const Ctx& c, const half* base, int kv_stride, int hs, int max_seq, int ti, int rows_total) {
     const int vsh = (hs == 128) ? 4 : (hs == 64) ? 3 : 2;  // log2(16-byte vectors per row)
-    const int total = nrows << vsh;
-    const half* src = base + (size_t)row0 * kv_stride;
-#pragma unroll
-    for (int r = 0; r < kAttnVecs; r++) {
-        const int idx = first + c.ctid + r * c.nthreads;
-        t.v[r] = make_uint4(0, 0, 0, 0);
-        if (idx < total) t.v[r] = ld_cg_v4(src + (size_t)(idx >> vsh) * kv_stride + (idx & ((1 << vsh) - 1)) * 8);
+    const int row0 = ti * kAttnTile;
+    int nrows = rows_total - row0;
+    if (nrows > kAttnTile) nrows = kAttnTile;
+    if (nrows > 0) {
+        const int total = nrows << vsh;
+        const uint32_t dst = attn_tile_buf(c, hs, max_seq, ti);
+        const half* src = base + (size_t)row0 * kv_stride;
+        for (int idx = c.ctid; idx < total; idx += c.nthreads)
+            cp_async16(dst + idx * 16, src + (size_t)(idx >> vsh) * kv_stride + (idx & ((1 << vsh) - 1)) * 8);
     }
+    cp_async_commit();
 }
-__device__ __forceinline__ void attn_tile_st(const Ctx& c, const TileRegs& t, uint32_t dst, int hs, int nrows, int first) {
-    const int vsh = (hs == 128) ? 4 : (hs == 64) ? 3 : 2;
-    const int total = nrows << vsh;
-#pragma unroll
-    for (int r = 0; r < kAttnVecs; r++) {
-        const int idx = first + c.ctid + r * c.nthreads;
-        if (idx < total) sts_v4_u32(dst + idx * 16, t.v[r]);
-    }
-}
-// rows [row0, row0 + nrows) of one head (hs halfs each, kv_stride apart) -> shared memory, row-major
-__device__ __forceinline__ void attn_load_tile(const Ctx& c, uint32_t dst, const half* base, int kv_stride, int hs, int row0, int nrows) {
-    const int vsh = (hs == 128) ? 4 : (hs == 64) ? 3 : 2;
-    const int total = nrows << vsh;
-#pragma unroll 1
-    for (int first = 0; first < total; first += kAttnVecs * c.nthreads) {
-        TileRegs t;
-        attn_tile_ld(c, t, base, kv_stride, hs, row0, nrows, first);
-        attn_tile_st(c, t, dst, hs, nrows, first);
-    }
-}
-// two tiles at once: both trips to L2 overlap
-__device__ __forceinline__ void attn_load_tiles2(const Ctx& c, uint32_t dst0, uint32_t dst1, const half* base, int kv_stride, int hs, int n0, int n1) {
-    const int vsh = (hs == 128) ? 4 : (hs == 64) ? 3 : 2;
-    const int total = (n0 > n1 ? n0 : n1) << vsh;
-#pragma unroll 1
-    for (int first = 0; first < total; first += kAttnVecs * c.nthreads) {
-        TileRegs t0, t1;
-        attn_tile_ld(c, t0, base, kv_stride, hs, 0, n0, first);
-        attn_tile_ld(c, t1, base, kv_stride, hs, kAttnTile, n1, first);
-        attn_tile_st(c, t0, dst0, hs, n0, first);
-        attn_tile_st(c, t1, dst1, hs, n1, first);
-    }
-}
-// Before the op's inputs are waited for: the first two K tiles of this CTA's (first) head.  Rows t < pos were written
-// by earlier launches, so they depend on nothing in this one.
 __device__ void attn_prefetch(const Ctx& c, const Op& op) {
     const int h = blockIdx.x, hs = op.head_size;
     if (h >= op.n_heads) return;
-    const int kvh = h / op.kv_mul;
-    const uint32_t bufA = c.sm.xs + attn_fixed_bytes(hs, op.max_seq), bufB = bufA + attn_buf_bytes(hs);
-    const half* kb = op.kcache + (size_t)kvh * hs;
-    const int n0 = c.pos < kAttnTile ? c.pos : kAttnTile, n1 = c.pos - kAttnTile < kAttnTile ? c.pos - kAttnTile : kAttnTile;
-    attn_load_tiles2(c, bufA, bufB, kb, op.kv_stride, hs, n0, n1 > 0 ? n1 : 0);
+    const half* kb = op.kcache + (size_t)(h / op.kv_mul) * hs;
+    for (int ti = 0; ti < kAttnAhead; ti++) attn_tile_async(c, kb, op.kv_stride, hs, op.max_seq, ti, c.pos);
 }
 
 template <int NSER>
@@ -1176,8 +1148,7 @@ __device__ void run_attn_t(Ctx& c, const Op& op, bool prefetched) {
     float* krow = qs + hs;                                  // hs: rotated k row of this step
     float* vrow = krow + hs;                                // hs: v row of this step
     float* att = vrow + hs;                                 // max_seq
-    const uint32_t bufA = c.sm.xs + attn_fixed_bytes(hs, op.max_seq), bufB = bufA + attn_buf_bytes(hs);
-    float* part = reinterpret_cast<float*>(c.scratch + attn_fixed_bytes(hs, op.max_seq));   // 32 * hs, aliases bufA
+    float* part = reinterpret_cast<float*>(c.scratch + attn_fixed_bytes(hs, op.max_seq));   // 32 * hs, aliases the first two tile buffers
     float* red = c.red;
     const int pos = c.pos, size = pos + 1;
 #pragma unroll 1
@@ -1185,7 +1156,9 @@ __device__ void run_attn_t(Ctx& c, const Op& op, bool prefetched) {
         const int kvh = h / op.kv_mul;
         half* kbase = op.kcache + (size_t)kvh * hs;
         const half* vbase = op.vcache + (size_t)kvh * hs;
-        const bool have_tile0 = prefetched && h == (int)blockIdx.x;
+        const int ntiles = (pos + kAttnTile - 1) / kAttnTile;
+        if (!(prefetched && h == (int)blockIdx.x))          // the first K tiles of the CTA's first head are already on their way
+            for (int ti = 0; ti < kAttnAhead; ti++) attn_tile_async(c, kbase, op.kv_stride, hs, op.max_seq, ti, pos);
         // ---- q, the new k row (rotated here when a table is given) and the new v row -> shared memory ----
         if (op.rope_tab != nullptr) {
             for (int i = tid; i < hs / 2; i += nt) {
@@ -1233,15 +1206,15 @@ __device__ void run_attn_t(Ctx& c, const Op& op, bool prefetched) {
             for (int i = tid; i < hs; i += nt)
                 vrow[i] = h2f_bits(op.vrawt != nullptr ? poll1(op.vrawt + (size_t)kvh * hs + i, c.tag_in) : ld_cg_u16(vbase + (size_t)pos * op.kv_stride + i));
         // ---- scores (lane chain over j = 32 i + lane, gpu_kernels.h:154-159), K tile by tile ----
+        // Copy groups: kAttnAhead are open when the loop starts and every iteration closes one more (tile ti + kAttnAhead, or an
+        // empty one), so "at most kAttnAhead - 1 groups pending" always means that this thread's part of tile ti has landed.
 #pragma unroll 1
-        for (int tile0 = 0; tile0 < pos; tile0 += kAttnTile) {
-            const int nrows = (pos - tile0 < kAttnTile) ? pos - tile0 : kAttnTile;
-            const uint32_t kbuf = (tile0 == kAttnTile) ? bufB : bufA;     // tiles 0 and 1 have their own buffer (prefetched), later ones reuse bufA
-            if (!(have_tile0 && tile0 <= kAttnTile)) {
-                named_bar(kBarAll, nt);                    // the previous tile is no longer read
-                attn_load_tile(c, kbuf, kbase, op.kv_stride, hs, tile0, nrows);
-            }
-            named_bar(kBarAll, nt);                        // tile (and, first time round, qs / krow / vrow) visible
+        for (int ti = 0; ti < ntiles; ti++) {
+            const int tile0 = ti * kAttnTile, nrows = (pos - tile0 < kAttnTile) ? pos - tile0 : kAttnTile;
+            cp_async_wait<kAttnAhead - 1>();
+            named_bar(kBarAll, nt);                        // tile ti is complete for everyone (first time round also qs / krow / vrow); tile ti-1 is no longer read
+            attn_tile_async(c, kbase, op.kv_stride, hs, op.max_seq, ti + kAttnAhead, pos);     // into the buffer tile ti-1 just left
+            const uint32_t kbuf = attn_tile_buf(c, hs, op.max_seq, ti);
 #pragma unroll 2
             for (int r = warp; r < nrows; r += c.nwc) {
                 const uint32_t row = kbuf + (uint32_t)r * hs * 2;
@@ -1262,9 +1235,9 @@ __device__ void run_attn_t(Ctx& c, const Op& op, bool prefetched) {
             sum = __fmul_rn(sum, op.att_alpha);
             if (lane == 0) att[pos] = __half2float(__float2half_rn(sum));
         }
-        // second V tile (if any) goes to bufA while the softmax runs: K is dead from here on
-        const int v1rows = (pos > kAttnTile) ? ((pos - kAttnTile < kAttnTile) ? pos - kAttnTile : kAttnTile) : 0;
-        attn_load_tiles2(c, bufB, bufA, vbase, op.kv_stride, hs, pos < kAttnTile ? pos : kAttnTile, v1rows);
+        // the first V tiles travel while the softmax runs: K is dead from here on (every warp is past the barrier above)
+        cp_async_wait<0>();
+        for (int ti = 0; ti < kAttnAhead; ti++) attn_tile_async(c, vbase, op.kv_stride, hs, op.max_seq, ti, pos);
         named_bar(kBarAll, nt);
         trace_mark(c, 3);
         // ---- softmax (idle reference threads seed the max with 0, gpu_kernels.h:374) ----
@@ -1305,28 +1278,25 @@ __device__ void run_attn_t(Ctx& c, const Op& op, bool prefetched) {
 #pragma unroll
             for (int q = 0; q < NS; q++) a[k][q] = 0.0f;
 #pragma unroll 1
-        for (int tile0 = 0, ti = 0; tile0 < pos; tile0 += kAttnTile, ti++) {
-            const int nrows = (pos - tile0 < kAttnTile) ? pos - tile0 : kAttnTile;
-            const uint32_t buf = (ti & 1) ? bufA : bufB;   // tile 0 in bufB, tile 1 in bufA, then alternating
-            if (ti >= 2) {
-                named_bar(kBarAll, nt);
-                attn_load_tile(c, buf, vbase, op.kv_stride, hs, tile0, nrows);
-                named_bar(kBarAll, nt);
-            }
+        for (int ti = 0; ti < ntiles; ti++) {
+            const int tile0 = ti * kAttnTile, nrows = (pos - tile0 < kAttnTile) ? pos - tile0 : kAttnTile;
+            cp_async_wait<kAttnAhead - 1>();
+            named_bar(kBarAll, nt);
+            attn_tile_async(c, vbase, op.kv_stride, hs, op.max_seq, ti + kAttnAhead, pos);
+            const uint32_t buf = attn_tile_buf(c, hs, op.max_seq, ti);
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const int tx = warp + k * c.nwc;
-                if (tx < 32) {
-                    for (int t = tile0 + tx; t < tile0 + nrows; t += 32) {     // kAttnTile % 32 == 0: t % 32 == tx
-                        const float pt = att[t];
-                        const uint32_t row = buf + (uint32_t)(t - tile0) * hs * 2 + lane * NS * 2;
+                if (tx < nrows) {                              // kAttnTile == 32: row tx of the tile is position t = tile0 + tx, t % 32 == tx
+                    const float pt = att[tile0 + tx];
+                    const uint32_t row = buf + (uint32_t)tx * hs * 2 + lane * NS * 2;
 #pragma unroll
-                        for (int q = 0; q < NS; q++) a[k][q] = __fmaf_rn(h2f_bits(lds_u16(row + q * 2)), pt, a[k][q]);
-                    }
+                    for (int q = 0; q < NS; q++) a[k][q] = __fmaf_rn(h2f_bits(lds_u16(row + q * 2)), pt, a[k][q]);
                 }
             }
         }
-        named_bar(kBarAll, nt);                            // tiles are dead: `part` may overwrite bufA
+        cp_async_wait<0>();
+        named_bar(kBarAll, nt);                            // tiles are dead: `part` may overwrite the tile buffers
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int tx = warp + k * c.nwc;
