@@ -137,7 +137,6 @@ constexpr int kMaxSlots = 64;
 constexpr int kBarAll = 13;        // named barrier: all consumer warps
 constexpr int kCtrlBytes = 4096;   // mbarriers (first 2 KB) + reduction scratch (at 3 KB)
 constexpr int kRedOffset = 3072;
-constexpr unsigned kSpinLimit = 1u << 24;
 constexpr unsigned long long kWaitLimitNs = 5000000000ull;   // a wait longer than 5 s is a protocol bug (or a dead peer): trap
 constexpr int kLapOffset = 2048;   // per-slot release counters (consumers), 64 words
 constexpr int kFillBaseOffset = 2304;   // per-slot fills before the current ring epoch (consumers), 64 words
@@ -159,13 +158,6 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
     asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    return done != 0;
-}
-// non-blocking probe (try_wait may suspend the whole warp for a system-defined time when the phase is not complete)
-__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                  : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     return done != 0;
 }
@@ -191,11 +183,6 @@ __device__ __forceinline__ void named_bar(int id, int nthreads) {
 __device__ __forceinline__ uint4 ld_cg_v4(const void* p) {   // L2-coherent (skips L1): data written by other CTAs
     uint4 r;
     asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ uint2 ld_cg_v2(const void* p) {
-    uint2 r;
-    asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
     return r;
 }
 __device__ __forceinline__ uint32_t ld_cg_u16(const void* p) {
@@ -264,11 +251,6 @@ __device__ __forceinline__ uint4 poll8(const uint32_t* p, uint32_t tag) {
 __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
     uint4 r;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
-    return r;
-}
-__device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
-    uint2 r;
-    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
     return r;
 }
 __device__ __forceinline__ void sts_v2_u32(uint32_t addr, uint2 v) {

@@ -33,11 +33,6 @@ __device__ __forceinline__ uint4 ldg_stream_v4(const void* p) {
         : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
-__device__ __forceinline__ uint2 ldg_stream_v2(const void* p) {
-    uint2 r;
-    asm("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
-    return r;
-}
 __device__ __forceinline__ uint32_t ldg_stream_u32(const void* p) {
     uint32_t r;
     asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
