@@ -1208,7 +1208,7 @@ __device__ void run_attn_t(Ctx& c, const Op& op, bool prefetched) {
                 if (lane == 0) att[tile0 + r] = __half2float(__float2half_rn(sum));
             }
         }
-        if (pos == 0 || true) named_bar(kBarAll, nt);      // krow visible (pos == 0: no tile loop ran); all tile reads done
+        named_bar(kBarAll, nt);                            // all tile reads done; krow visible even when no tile loop ran (pos == 0)
         if (warp == 0) {                                   // the row of this step
             float sum = 0.0f;
 #pragma unroll
