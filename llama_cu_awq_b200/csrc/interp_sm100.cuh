@@ -1,25 +1,30 @@
-// interp_sm100.cuh -- the persistent decode kernel for sm_100a ("op interpreter"), v3.
+// interp_sm100.cuh -- the persistent decode kernel for sm_100a ("op interpreter").
 //
 // One launch walks a table of ops (the whole per-token forward pass of llama2_q4.cu:286-340 plus the
-// greedy sampler, or a single op for the operator API) with ONE CTA PER SM:
+// greedy sampler, or a single op for the operator API) with ONE CTA PER SM, 11 consumer warps + 1 producer warp:
 //
-//   * a PRODUCER warp streams every weight byte the CTA will need with 1-D TMA bulk copies
-//     (cp.async.bulk + mbarrier complete_tx) into PER-CONSUMER-WARP rings of shared-memory slots.
-//     Weights never depend on activations, so the producer runs ahead across op boundaries and grid
-//     barriers: HBM keeps streaming while the consumers wait on a dependency.  Producer lane l feeds
-//     consumer warp l, so no consumer ever waits for another warp's data.
+//   * the PRODUCER lane streams every weight byte the CTA will need with 1-D TMA bulk copies
+//     (cp.async.bulk + mbarrier complete_tx) into ONE FIFO ring of shared-memory slots, a slot being a run of
+//     whole columns (4-11 KB: the TMA unit sustains about one copy per 70 cycles per SM, so copies must be
+//     large).  Weights never depend on activations, so the producer runs ahead across op boundaries: HBM keeps
+//     streaming while the consumers wait on a dependency.  The slot size is per op ("ring epochs"); scales and
+//     zero points of the CTA's column range travel the same way into a ping-pong pair of buffers.
 //   * each CONSUMER warp owns whole output columns: a warp-task is 4 columns (two per half-warp) of an
-//     INT4 matrix, or 2 gate/up column pairs, or 4 classifier rows, streamed trip by trip
+//     INT4 matrix, or 2 gate/up column pairs, or 1-4 classifier rows, streamed trip by trip
 //     (1024 k per trip, the reference's loop trip, gpu_kernels.h:176-201).  There is NO inter-warp
 //     synchronisation inside an op: the accumulators of a column stay in one thread's registers from the
 //     first trip to the last, which keeps every per-lane FMA chain of the reference in its original order
-//     (results are bit-identical) and makes the consumers issue-bound instead of latency-bound.
+//     (results are bit-identical).
 //   * one thread owns TWO reference lanes (2j, 2j+1) of two columns: one packed FFMA2 (fma.rn.f32x2)
 //     advances both lane chains of a column with a natural (x[k], x[k+32]) register pair that is read
 //     from shared memory once and used for both columns.  The activation vector is staged per op into
-//     shared memory as fp32 pairs in exactly that order (after the fused RMSNorm).
-//   * ops are separated by a grid-wide barrier (release/acquire counter in global memory) only where
-//     the dataflow needs one.
+//     shared memory as fp32 pairs in exactly that order; a fused RMSNorm is computed on the way, in registers,
+//     in the reference's summation order (stage_norm).
+//   * ACTIVATIONS CARRY THEIR OWN SYNCHRONISATION ("flag-in-data"): every element travels as one 32-bit word
+//     tag<<16 | fp16, the tag naming the op and launch that wrote it; a reader re-reads a word until the tag is
+//     the expected one.  No grid barrier separates two ops, except in front of the argmax.
+//   * attention runs one head per CTA; K and V rows stream through a four-deep ring of 32-row tiles filled by
+//     cp.async (run_attn_t).
 //
 // INT4 dequantisation: see kernels_sm100.cuh (LOP3 -> FHFMA -> FFMA2, exact).
 #pragma once
