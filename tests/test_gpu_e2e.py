@@ -55,12 +55,14 @@ def run_steps(lib_step, reset, prompt, n_steps, vocab, free_run):
     return logits, out
 
 
-@pytest.mark.parametrize("cfg_name", ["TINY", "TINY_GQA", "SMALL"])
+@pytest.mark.parametrize("cfg_name", ["TINY", "TINY_GQA", "SMALL", "SMALL_LONG"])
 def test_logits_bit_identical_to_reference(eng, cfg_name):
     E, lib = eng
     r = H.ref()
     if r is None:
         pytest.skip("oracle/_ref/libq4ref.so not built")
+    long_run = cfg_name == "SMALL_LONG"       # 500 positions: 16 tiles through the four-deep K/V ring of the fused attention
+    cfg_name = "SMALL" if long_run else cfg_name
     cfg = getattr(H, cfg_name)
     with tempfile.TemporaryDirectory() as d:
         path = os.path.join(d, "m.bin")
@@ -70,12 +72,12 @@ def test_logits_bit_identical_to_reference(eng, cfg_name):
         try:
             vocab = cfg["vocab_size"]
             # TINY runs long enough for three K/V tiles of the fused attention (positions up to 220)
-            n_steps = min(220 if cfg_name == "TINY" else 96, cfg["seq_len"] - 1)
+            n_steps = min(500 if long_run else 220 if cfg_name == "TINY" else 96, cfg["seq_len"] - 1)
             # 1) reference free-running greedy from a 3-token prompt
             prompt = [1, 35, 72]
             ref_logits, ref_toks = run_steps(lambda g, l, n: r.ref_step(g, l, n), r.ref_reset, prompt, n_steps, vocab, True)
             assert np.isfinite(ref_logits.view(np.float16).astype(np.float32)).all(), "synthetic model produced inf/NaN"
-            for fused in (1, 0):
+            for fused in ((1,) if long_run else (1, 0)):
                 lib.lq4_set_option(b"fused", fused)
                 # 2) ours, teacher-forced with the reference's tokens: logits must match bit for bit
                 forced = ref_toks[: n_steps + 1]
