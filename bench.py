@@ -2,24 +2,32 @@
 """bench.py -- decode tokens/sec of Llama-2-7B AWQ-w4-g128 (random-init, synthetic) on B200.
 
 Contract (one JSON line on stdout, rank 0):
-  python bench.py --gpus N --steps K --warmup W [--impl reference] [--model 7b|13b|tiny]
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--model 7b|13b|tiny] [--parallelism tp|replicas]
 
 A "step" is one decode forward + greedy sample (seq_len=1) at consecutive positions 0..K-1 of the
 workload `Llama-2-7B w4-g128 random-init .bin, greedy decode` (BASELINE.json configs[1]); the default
 K=256 is the reference's `-n 256`.
 
   value  : tokens/s with everything resident in HBM, K steps enqueued back to back on the engine
-           stream (position and token live on the device), timed with CUDA events on that stream.
+           stream (position and token live on the device), timed with CUDA events on that stream,
+           max over ranks.
+           N = 1: one GPU.   N > 1 (default --parallelism tp): ONE stream decoded tensor-parallel over
+           N GPUs (BASELINE.json configs[3], "scaling": "strong"); the ids of the TP run are compared
+           IN THIS RUN with the ids the same ranks produce on one GPU (`tp.ids_match_single_gpu`), and
+           the N independent replicas measured in the same run are reported beside it (`replicas`).
   e2e    : tokens/s through the C-ABI host-buffer call lq4_generate_tokens (prompt tokens in host
            memory, ids out to host memory; the per-token pinned-memory token/position hand-off and the
-           host wait are inside its timed loop, as in the reference's generate()).
+           host wait are inside its timed loop, as in the reference's generate(); ns clock).
   roofline: dominant kernel = interp_kernel, the persistent kernel that IS the decode step (one launch per
-           token): algorithmic bytes (weights + KV) / mean launch duration against MEASURED_PEAKS.json;
-           roofline_ffn_op is the largest single op (gate/up+SiLU) alone through the operator API.
-  cpu_baseline: the oracle port (oracle/cpu_ref.c) single-threaded on a bounded sample.
---impl reference: the reference has no CPU implementation (CUDA only), so this arm times the oracle
-  port with all host threads on a bounded sample, and also reports the UNMODIFIED reference CUDA build
-  (oracle/_ref/llama2_q4_ref) run on the same GPU/.bin as `reference_cuda` (its own achieved tok/s line).
+           token): algorithmic bytes (weights + KV) / mean launch duration against MEASURED_PEAKS.json.
+  cpu_baseline: the oracle port (oracle/cpu_ref.c) single-threaded on REAL tokens (all layers, positions
+           0..1, KV cache and attention included); `cpu_baseline_all_threads` the same on every host core.
+--impl reference: the reference is a CUDA program with no CPU path, so this arm times the UNMODIFIED
+  reference (oracle/_ref/libq4ref.so = its translation unit behind a C shim, built by oracle/build_ref.sh)
+  on the same GPU and `.bin`: its own loop body (cudaStreamSynchronize + run_transformer, llama2_q4.cu:
+  465-470) for K steps in steady state (graphs already captured), CUDA events on its stream.  It maps
+  neither libllama_q4_b200.so nor the oracle into the timed process state beyond the CPU-port side record
+  (`cpu_baseline`: the oracle port on all host threads over 3 real tokens, measured, not extrapolated).
 """
 import argparse
 import ctypes as C
@@ -36,6 +44,15 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 PROMPT = "hello"
+SEED = 0x5EED
+METRIC = "decode tokens/sec (seq_len=1)"
+DTYPE = "int4 weights, fp16 storage, fp32 accumulate"
+
+MODELS = {
+    "7b": dict(dim=4096, hidden_dim=11008, n_layers=32, n_heads=32, n_kv_heads=32, vocab_size=32000, seq_len=2048, rope_theta=10000.0),
+    "13b": dict(dim=5120, hidden_dim=13824, n_layers=40, n_heads=40, n_kv_heads=40, vocab_size=32000, seq_len=2048, rope_theta=10000.0),
+    "tiny": dict(dim=1024, hidden_dim=2816, n_layers=3, n_heads=8, n_kv_heads=8, vocab_size=2048, seq_len=512, rope_theta=10000.0),
+}
 
 
 def load_peaks():
@@ -47,34 +64,50 @@ def load_peaks():
 
 
 def model_cfg(name):
-    import llama_cu_awq_b200 as E
-    import helpers as H
-    return {"7b": E.LLAMA2_7B, "13b": E.LLAMA2_13B, "tiny": H.SMALL}[name]
+    return dict(MODELS[name])
 
 
-def scratch_dir():
+def scratch_dir(need=10 << 30):
     for d in ("/dev/shm", "/tmp"):
         try:
             st = os.statvfs(d)
-            if st.f_bavail * st.f_frsize > 10 << 30:
+            if st.f_bavail * st.f_frsize > need:
                 return d
         except OSError:
             pass
     return "/tmp"
 
 
-def ensure_files(lib, E, name, cfg, rank=0):
+def synth_paths(name, cfg):
     d = scratch_dir()
-    path = os.path.join(d, f"lq4_synth_{name}.bin")
-    tok = os.path.join(d, f"lq4_synth_tok_{cfg['vocab_size']}.bin")
-    c = E.Config(**cfg)
+    for cand in ("/dev/shm", "/tmp"):       # a file written earlier in this box's life wins over free-space heuristics
+        if os.path.exists(os.path.join(cand, f"lq4_synth_{name}.bin.ok")):
+            d = cand
+            break
+    return os.path.join(d, f"lq4_synth_{name}.bin"), os.path.join(d, f"lq4_synth_tok_{cfg['vocab_size']}.bin")
+
+
+def ensure_files(lib, E, name, cfg, rank=0):
+    """Synthetic `.bin` + tokenizer (seeded).  `lib` may be None: then the stand-alone writer
+    llama_cu_awq_b200/gen_synth_bin (same synth.h, same bytes) is used and the engine is never loaded."""
+    path, tok = synth_paths(name, cfg)
     if rank == 0:
+        tool = os.path.join(ROOT, "llama_cu_awq_b200", "gen_synth_bin")
         if not os.path.exists(path + ".ok"):
-            n = lib.lq4_write_synth_model(path.encode(), C.byref(c), 0x5EED)
+            if lib is not None:
+                c = E.Config(**cfg)
+                n = lib.lq4_write_synth_model(path.encode(), C.byref(c), SEED)
+            else:
+                r = subprocess.run([tool, "model", path] + [str(cfg[k]) for k in ("dim", "hidden_dim", "n_layers", "n_heads", "n_kv_heads", "vocab_size", "seq_len", "rope_theta")] + [str(SEED)],
+                                   capture_output=True, text=True, check=True)
+                n = int(r.stdout.strip())
             assert n == os.path.getsize(path) and n > 0
             open(path + ".ok", "w").write(str(n))
         if not os.path.exists(tok):
-            assert lib.lq4_write_synth_tokenizer(tok.encode(), cfg["vocab_size"]) > 0
+            if lib is not None:
+                assert lib.lq4_write_synth_tokenizer(tok.encode(), cfg["vocab_size"]) > 0
+            else:
+                subprocess.run([tool, "tokenizer", tok, str(cfg["vocab_size"])], capture_output=True, check=True)
     return path, tok
 
 
@@ -118,31 +151,29 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_baseline_sample(path, cfg, threads):
-    """Oracle port on the host: one token at pos 0 through `nl` layers, scaled to the full depth plus the
-    classifier measured separately (bounded to ~10-30 s)."""
+def cpu_port_tokens(path, cfg, threads, n_tokens):
+    """Oracle port on the host, REAL tokens: every layer, the classifier, KV cache and attention, at positions
+    0..n_tokens-1 (greedy chain from BOS).  Measured, nothing extrapolated."""
     import numpy as np
     import helpers as H
     o = H.oracle()
     o.oracle_set_threads(threads)
     m = o.oracle_model_open(path.encode())
     assert m, "oracle could not map the .bin"
-    nl = 1 if threads == 1 else min(4, cfg["n_layers"])
-    t0 = time.perf_counter()
-    o.oracle_model_forward(m, 1, 0, None, nl)
-    t_layers = time.perf_counter() - t0
     lg = np.zeros(cfg["vocab_size"], np.uint16)
+    tok = 1
     t0 = time.perf_counter()
-    o.oracle_model_forward(m, 1, 0, H.ptr(lg), 0)
-    t_cls = time.perf_counter() - t0
+    for pos in range(n_tokens):
+        o.oracle_model_forward(m, tok, pos, H.ptr(lg), -1)
+        tok = int(o.oracle_argmax(H.ptr(lg), cfg["vocab_size"]))
+    dt = time.perf_counter() - t0
     o.oracle_model_close(m)
-    per_token = t_layers / nl * cfg["n_layers"] + t_cls
-    return {"value": 1.0 / per_token, "unit": "tokens/s", "cores": threads, "kind": "port",
-            "sample": f"1 token at pos 0: {nl} of {cfg['n_layers']} layers ({t_layers:.2f}s) scaled to full depth + classifier ({t_cls:.2f}s), oracle/cpu_ref.c"}
+    return {"value": n_tokens / dt, "unit": "tokens/s", "cores": threads, "kind": "port",
+            "sample": f"{n_tokens} real token(s) at positions 0..{n_tokens - 1}: all {cfg['n_layers']} layers + attention + classifier + argmax, {dt:.2f} s, oracle/cpu_ref.c"}
 
 
 def max_over_ranks(value, world, device="cuda"):
-    """Replicas: the job's time is the slowest rank's (max over ranks); a plain float in, a plain float out."""
+    """The job's time is the slowest rank's (max over ranks); a plain float in, a plain float out."""
     if world <= 1:
         return float(value)
     import torch
@@ -152,48 +183,187 @@ def max_over_ranks(value, world, device="cuda"):
     return float(t.item())
 
 
+def min_over_ranks(value, world, device="cuda"):
+    if world <= 1:
+        return float(value)
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(value)], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return float(t.item())
+
+
 def aggregate_throughput(units_per_rank, seconds, world, device="cuda"):
     """Whole-job throughput of `world` independent replicas: all units / the slowest rank's time."""
     return world * units_per_rank / max_over_ranks(seconds, world, device)
 
 
+# ----------------------------------------------------------------------------------------------- reference arm
 def run_reference_arm(args):
-    import llama_cu_awq_b200 as E
-    lib = E.lib()
-    cfg = model_cfg(args.model)
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    path, tok = ensure_files(lib, E, args.model, cfg)
-    threads = os.cpu_count() or 1
-    base = cpu_baseline_sample(path, cfg, threads)
-    out = {"metric": "decode tokens/sec (seq_len=1)", "impl": "reference", "value": base["value"], "unit": "tokens/s",
-           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / base["value"],
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int4 weights, fp16 storage, fp32 accumulate",
-           "data": "synthetic", "config": {"workload": f"Llama-2-{args.model.upper()} w4-g128 random-init .bin, greedy decode"},
-           "cpu_baseline": base,
-           "e2e": {"value": base["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "note": "the reference is CUDA-only (no CPU path, SURVEY.md 8d): this arm is the oracle port on all host threads; "
-                   "reference_cuda is the unmodified reference built for sm_100a run on this GPU"}
-    ref_bin = os.path.join(ROOT, "oracle", "_ref", "llama2_q4_ref")
+    import helpers as H
+    cfg = model_cfg(args.model)
+    path, tok = ensure_files(None, None, args.model, cfg)
+    K = max(1, min(args.steps, cfg["seq_len"] - 1))
+    W = max(3, args.warmup)
     try:
         import torch
         has_gpu = torch.cuda.is_available()
     except Exception:
         has_gpu = False
-    if os.path.exists(ref_bin) and has_gpu:
-        n = max(2, min(args.steps if args.steps > 0 else 256, cfg["seq_len"]))
-        best = None
-        for _ in range(2):   # first run pays page-cache / driver warm-up
-            r = subprocess.run([ref_bin, path, "-z", tok, "-t", "0", "-n", str(n), "-i", PROMPT], capture_output=True, text=True, timeout=900)
-            mt = re.search(r"achieved tok/s: ([0-9.]+)\. Tokens: (\d+), seconds: ([0-9.eE+-]+)", r.stdout)
-            if mt and (best is None or float(mt.group(1)) > best["value"]):
-                best = {"value": float(mt.group(1)), "unit": "tokens/s", "tokens": int(mt.group(2)), "seconds": float(mt.group(3)),
-                        "how": f"oracle/_ref/llama2_q4_ref <bin> -t 0 -n {n}: its own 'achieved tok/s' line (wall clock incl. graph capture), best of 2"}
-        out["reference_cuda"] = best if best else {"unavailable": (r.stderr or r.stdout)[-200:]}
-    else:
-        out["reference_cuda"] = {"unavailable": "no GPU or oracle/_ref/llama2_q4_ref not built"}
+    r = H.ref() if has_gpu else None
+    if r is None:
+        # the reference is CUDA-only: without a GPU (or without oracle/_ref, built by oracle/build_ref.sh) there is nothing to time
+        print(json.dumps({"impl": "reference", "unavailable": "no CUDA device" if not has_gpu else "oracle/_ref/libq4ref.so is missing (run __graft_entry__.build() where /root/reference exists)"}), flush=True)
+        sys.exit(0 if not has_gpu else 1)
+    assert r.ref_open(path.encode()) == 0
+    bos = (C.c_int * 1)(1)
+    # pass 1 (untimed): the same positions, so that every length bin's graph is captured; also the warm-up
+    r.ref_reset(bos, 1)
+    r.ref_time_steps(max(W, K), 0)
+    # pass 2 (timed): steady state
+    clocks = ClockSampler(0)
+    clocks.start()
+    r.ref_reset(bos, 1)
+    t0 = time.perf_counter()
+    ms = float(r.ref_time_steps(K, 0))
+    wall = time.perf_counter() - t0
+    clk = clocks.stop()
+    ids = [int(r.ref_token_at(i)) for i in range(min(K + 1, 17))]
+    r.ref_close()
+    value = K / (ms * 1e-3)
+    out = {"metric": METRIC, "impl": "reference", "value": value, "unit": "tokens/s", "n_gpus": 1, "steps": K, "warmup": W,
+           "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+           "config": {"workload": f"Llama-2-{args.model.upper()} w4-g128 random-init .bin, greedy decode -n {K}, batch 1",
+                      "l2": "inputs larger than L2 (3.6 GB of weights per step)", "parallelism": "1 GPU (the reference has no multi-GPU path)"},
+           "clocks": clk,
+           "e2e": {"value": K / wall, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                   "how": "host wall clock around the same K-step loop (the loop synchronises the stream before every launch, as generate() does)"},
+           "how": "UNMODIFIED reference TU (oracle/_ref/libq4ref.so): its loop body cudaStreamSynchronize + run_transformer (llama2_q4.cu:465-470), "
+                  "K steps in steady state after a pass that captured its CUDA graphs, CUDA events on its stream; 323 graph nodes + 1 sampler launch per token",
+           "first_ids": ids}
+    # the reference's own CLI line on the same file (wall clock incl. graph capture and console I/O), for context
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "llama2_q4_ref")
+    if os.path.exists(ref_bin):
+        n = max(2, min(K, cfg["seq_len"]))
+        rr = subprocess.run([ref_bin, path, "-z", tok, "-t", "0", "-n", str(n), "-i", PROMPT], capture_output=True, text=True, timeout=900)
+        mt = re.search(r"achieved tok/s: ([0-9.]+)\. Tokens: (\d+), seconds: ([0-9.eE+-]+)", rr.stdout)
+        out["reference_cli"] = ({"value": float(mt.group(1)), "unit": "tokens/s", "tokens": int(mt.group(2)), "seconds": float(mt.group(3)),
+                                 "how": f"oracle/_ref/llama2_q4_ref <bin> -t 0 -n {n}: its own 'achieved tok/s' line"} if mt else {"unavailable": (rr.stderr or rr.stdout)[-200:]})
+    if not args.no_cpu_baseline:
+        try:
+            out["cpu_baseline"] = cpu_port_tokens(path, cfg, os.cpu_count() or 1, 3)
+            out["cpu_baseline"]["note"] = "side record: the reference has no CPU implementation; the line's value is the reference CUDA build"
+        except Exception as e:
+            out["cpu_baseline"] = {"unavailable": str(e)[:200]}
     print(json.dumps(out), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+class Engine:
+    def __init__(self, E, lib, path, cfg, rank, world, tp):
+        import torch
+        self.E, self.lib, self.cfg, self.tp = E, lib, cfg, tp
+        assert lib.lq4_tp_config(rank if tp else 0, world if tp else 1) == 0
+        self.t = E.Transformer()
+        lib.lq4_build_transformer(C.byref(self.t), path.encode(), 0)
+        self.s = E.Sampler()
+        lib.lq4_build_sampler(C.byref(self.s), cfg["vocab_size"], 0.0, 0.9, 1)
+        if tp:
+            E.tp_connect(lib, self.t, rank, world)     # CUDA IPC handles of the ranks' activation buffers, exchanged over torch.distributed
+        self.stream = torch.cuda.ExternalStream(lib.lq4_get_stream())
+        self.bos = (C.c_int * 1)(1)
+
+    def enqueue(self, n_steps):
+        self.lib.lq4_reset(C.byref(self.t), self.bos, 1)
+        for i in range(n_steps):
+            self.lib.lq4_enqueue_step(C.byref(self.t), C.byref(self.s), i + 1, 1)
+
+    def warm(self, K, W):
+        seq = self.cfg["seq_len"]
+        self.enqueue(min(seq - 1, max(W, 130 if K > 128 else W)))
+        if K > 256:
+            self.enqueue(K)
+        assert self.lib.lq4_stream_synchronize() == 0
+
+    def timed(self, K, barrier):
+        """K steps back to back, CUDA events on the engine stream; returns (ms, ids[0..K])."""
+        import torch
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        self.lib.lq4_reset(C.byref(self.t), self.bos, 1)
+        ev0.record(self.stream)
+        for i in range(K):
+            self.lib.lq4_enqueue_step(C.byref(self.t), C.byref(self.s), i + 1, 1)
+        ev1.record(self.stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        ids = [int(self.t.state.shared_data.contents.tokens[i]) for i in range(K + 1)]
+        return ms, ids
+
+    def e2e(self, K, barrier):
+        out = (C.c_int * (K + 1))()
+        secs = C.c_double(0)
+        barrier()
+        n = self.lib.lq4_generate_tokens(C.byref(self.t), C.byref(self.s), self.bos, 1, K + 1, out, C.byref(secs), 1)
+        return n, secs.value, list(out)
+
+    def close(self):
+        self.lib.lq4_destroy_sampler(C.byref(self.s))
+        self.lib.lq4_free_transformer(C.byref(self.t))
+
+
+def op_timings(eng, lib, E, cfg, peak):
+    """Single operators through the operator API (launch overhead included), all layers' weights in rotation (> L2 for gate/up)."""
+    import torch
+    d, h, L = cfg["dim"], cfg["hidden_dim"], cfg["n_layers"]
+    t, stream = eng.t, eng.stream
+    layers = t.weights.layers
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+
+    def time_op(fn):
+        for l in range(L):
+            fn(l)
+        torch.cuda.synchronize()
+        ev0.record(stream)
+        for _ in range(reps):
+            for l in range(L):
+                fn(l)
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) * 1000.0 / (reps * L)
+
+    ffn_bytes = 2 * h * (E.packed_weight_height(d) * 4 + E.packed_zeros_height(d) * 4 + E.num_groups(d) * 2)
+    ffn_us = time_op(lambda l: lib.lq4_ffn_matvec_silu(t.state.hb, t.state.xb, C.byref(layers[l].wq_gate), C.byref(layers[l].wq_up), d, h))
+    ach = ffn_bytes / (ffn_us * 1e-6) / 1e9
+    roofline_ffn = {"bound": "hbm", "kernel": "single op lq4_ffn_matvec_silu (K=%d N=%d) through the operator API, launch overhead included" % (d, h),
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "bytes_per_launch": ffn_bytes, "us_per_launch": ffn_us}
+    # BASELINE.json configs[0]: single INT4 GEMV M=1 K=N=dim g128 (the o-projection), one matrix per layer in rotation (32 x 8.7 MB > L2)
+    gemv_bytes = d * (E.packed_weight_height(d) * 4 + E.packed_zeros_height(d) * 4 + E.num_groups(d) * 2)
+    gemv_us = time_op(lambda l: lib.lq4_matmul_q4(t.state.x, t.state.xb, C.byref(layers[l].wq_o), d, d, 0, -1, None))
+    gemv_op = {"kernel": "single op lq4_matmul_q4 (K=N=%d g128) through the operator API, launch overhead included" % d, "bytes_per_launch": gemv_bytes,
+               "us_per_launch": gemv_us, "achieved": gemv_bytes / (gemv_us * 1e-6) / 1e9, "unit": "GB/s", "peak": peak,
+               "frac": gemv_bytes / (gemv_us * 1e-6) / 1e9 / peak}
+    return roofline_ffn, gemv_op
+
+
+def roofline_record(E, cfg, model, K, ms, peak, peak_src, share=1):
+    wbytes = E.weight_bytes_per_token(cfg)
+    kvbytes = sum(E.kv_bytes_at(cfg, p) for p in range(K)) / K
+    gbs = (wbytes + kvbytes) / share / (ms / K * 1e-3) / 1e9      # per GPU: each tensor-parallel rank streams 1/share of the bytes
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "step_traffic.json")
+    if os.path.exists(tpath) and share == 1:
+        with open(tpath) as f:
+            traffic = json.load(f).get(model, {}).get("dram_bytes_per_launch")
+    return {"bound": "hbm", "kernel": "interp_kernel (whole decode step: 1 launch per token)", "achieved": gbs, "peak": peak,
+            "unit": "GB/s", "frac": gbs / peak, "traffic": traffic, "bytes_per_launch": (wbytes + kvbytes) / share,
+            "us_per_launch": ms / K * 1000.0, "peak_source": peak_src,
+            "how": "algorithmic bytes (weights + mean KV over the K positions) / mean launch duration, CUDA events on the engine stream; "
+                   "traffic = dram read+write of one launch from the committed ncu --set full capture (profiles/step_traffic.json)"}
 
 
 def main():
@@ -204,14 +374,14 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--model", default="7b")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--parallelism", default="replicas", choices=["replicas", "tp"],
-                    help="N>1: independent replicas (weak scaling, default) or tensor-parallel decode of ONE stream (strong scaling)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the 13B, op-by-op and single-operator side records of the N=1 line")
+    ap.add_argument("--parallelism", default="tp", choices=["tp", "replicas"],
+                    help="N>1: tensor-parallel decode of ONE stream (strong scaling, default; replicas are measured beside it) or replicas only")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
         return
 
-    import numpy as np
     import torch
     import llama_cu_awq_b200 as E
 
@@ -227,36 +397,10 @@ def main():
     lib = E.lib()
     assert lib.lq4_init(local_rank) == 0
     tp = world > 1 and args.parallelism == "tp"
-    if tp:
-        assert lib.lq4_tp_config(rank, world) == 0
     cfg = model_cfg(args.model)
     K = max(1, min(args.steps, cfg["seq_len"] - 1))
     W = max(3, args.warmup)
     path, tok = ensure_files(lib, E, args.model, cfg, rank)
-    if world > 1:
-        dist.barrier()
-
-    t = E.Transformer()
-    lib.lq4_build_transformer(C.byref(t), path.encode(), 0)
-    s = E.Sampler()
-    lib.lq4_build_sampler(C.byref(s), cfg["vocab_size"], 0.0, 0.9, 1)
-    if tp:
-        E.tp_connect(lib, t, rank, world)     # CUDA IPC handles of the ranks' activation buffers, exchanged over torch.distributed
-    stream = torch.cuda.ExternalStream(lib.lq4_get_stream())
-    bos = (C.c_int * 1)(1)
-
-    def enqueue(n_steps):
-        lib.lq4_reset(C.byref(t), bos, 1)
-        for i in range(n_steps):
-            lib.lq4_enqueue_step(C.byref(t), C.byref(s), i + 1, 1)
-
-    # ---- warm-up ----
-    if world > 1:
-        dist.barrier()
-    enqueue(min(cfg["seq_len"] - 1, max(W, 130 if K > 128 else W)))
-    if K > 256:
-        enqueue(K)
-    assert lib.lq4_stream_synchronize() == 0
 
     def barrier():
         torch.cuda.synchronize()
@@ -264,116 +408,105 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- value: K steps back to back, device-timed on the engine stream ----
-    clocks = ClockSampler(local_rank)
     barrier()
-    clocks.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    lib.lq4_reset(C.byref(t), bos, 1)
-    with torch.cuda.stream(stream):
-        ev0.record(stream)
-    for i in range(K):
-        lib.lq4_enqueue_step(C.byref(t), C.byref(s), i + 1, 1)
-    with torch.cuda.stream(stream):
-        ev1.record(stream)
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    ms = max_over_ranks(ms, world)
-    tokens_dev = [int(t.state.shared_data.contents.tokens[i]) for i in range(K + 1)]
-
-    # ---- e2e: the host-buffer API, wall clock inside the call (host wait + pinned hand-off per token) ----
-    out = (C.c_int * (K + 1))()
-    secs = C.c_double(0)
-    barrier()
-    n = lib.lq4_generate_tokens(C.byref(t), C.byref(s), bos, 1, K + 1, out, C.byref(secs), 1)
-    e2e_val = (n - 1) / secs.value if secs.value > 0 else None
-    assert list(out)[1:n] == tokens_dev[1:n], "pipelined host API and raw enqueue disagree on token ids"
-    if world > 1:
-        e2e_val = (n - 1) / max_over_ranks(secs.value, world)
-    clk = clocks.stop()             # sampled across both timed regions (device-timed steps and the end-to-end call)
-    units = 1 if tp else world        # tensor parallel: all ranks decode ONE stream; replicas: one stream each
-
-    # ---- roofline ----
-    # The decode step is ONE launch of the persistent kernel (interp_kernel), so the dominant kernel's launch
-    # duration is ms/K measured above with CUDA events on the engine stream.  Algorithmic bytes per launch =
-    # weights + KV cache rows touched (DESIGN.md "bytes per unit"), averaged over the K positions.
     peak, peak_src = load_peaks()
-    d, h, L = cfg["dim"], cfg["hidden_dim"], cfg["n_layers"]
-    wbytes = E.weight_bytes_per_token(cfg)
-    kvbytes = sum(E.kv_bytes_at(cfg, p) for p in range(K)) / K
-    step_gbs = (wbytes + kvbytes) / (ms / K * 1e-3) / 1e9 / (world if tp else 1)     # per GPU: each rank streams 1/world of the bytes
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "step_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            traffic = json.load(f).get(args.model, {}).get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "interp_kernel (whole decode step: 1 launch per token)", "achieved": step_gbs, "peak": peak,
-                "unit": "GB/s", "frac": step_gbs / peak, "traffic": traffic, "bytes_per_launch": wbytes + kvbytes,
-                "us_per_launch": ms / K * 1000.0, "peak_source": peak_src,
-                "how": "algorithmic bytes (weights + mean KV over the K positions) / mean launch duration, CUDA events on the engine stream; "
-                       "traffic = dram read+write of one launch from the committed ncu --set full capture (profiles/)"}
-    # the largest single op (gate/up+SiLU INT4 GEMV, 45% of a layer's bytes) alone through the operator API, all layers' weights in rotation
-    ffn_bytes = 2 * h * (E.packed_weight_height(d) * 4 + E.packed_zeros_height(d) * 4 + E.num_groups(d) * 2)
-    layers = t.weights.layers
-    reps = 3
-    for _ in range(2):
-        for l in range(L):
-            lib.lq4_ffn_matvec_silu(t.state.hb, t.state.xb, C.byref(layers[l].wq_gate), C.byref(layers[l].wq_up), d, h)
-    torch.cuda.synchronize()
-    with torch.cuda.stream(stream):
-        ev0.record(stream)
-    for _ in range(reps):
-        for l in range(L):
-            lib.lq4_ffn_matvec_silu(t.state.hb, t.state.xb, C.byref(layers[l].wq_gate), C.byref(layers[l].wq_up), d, h)
-    with torch.cuda.stream(stream):
-        ev1.record(stream)
-    torch.cuda.synchronize()
-    ffn_us = ev0.elapsed_time(ev1) * 1000.0 / (reps * L)
-    ach = ffn_bytes / (ffn_us * 1e-6) / 1e9
-    roofline_ffn = {"bound": "hbm", "kernel": "interp_kernel, single op lq4_ffn_matvec_silu (K=%d N=%d), launch overhead included" % (d, h),
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "bytes_per_launch": ffn_bytes, "us_per_launch": ffn_us}
-    # BASELINE.json configs[0]: single INT4 GEMV M=1 K=N=4096 g128 (the o-projection), one matrix per layer in rotation
-    # (32 x 8.7 MB > L2 would be needed for a cold number; 7B has exactly 32 such matrices = 279 MB)
-    gemv_bytes = d * (E.packed_weight_height(d) * 4 + E.packed_zeros_height(d) * 4 + E.num_groups(d) * 2)
-    for l in range(L):
-        lib.lq4_matmul_q4(t.state.x, t.state.xb, C.byref(layers[l].wq_o), d, d, 0, -1, None)
-    torch.cuda.synchronize()
-    with torch.cuda.stream(stream):
-        ev0.record(stream)
-    for _ in range(reps):
-        for l in range(L):
-            lib.lq4_matmul_q4(t.state.x, t.state.xb, C.byref(layers[l].wq_o), d, d, 0, -1, None)
-    with torch.cuda.stream(stream):
-        ev1.record(stream)
-    torch.cuda.synchronize()
-    gemv_us = ev0.elapsed_time(ev1) * 1000.0 / (reps * L)
-    gemv_op = {"kernel": "interp_kernel, single op lq4_matmul_q4 (K=N=%d g128), launch overhead included" % d, "bytes_per_launch": gemv_bytes,
-               "us_per_launch": gemv_us, "achieved": gemv_bytes / (gemv_us * 1e-6) / 1e9, "unit": "GB/s", "peak": peak,
-               "frac": gemv_bytes / (gemv_us * 1e-6) / 1e9 / peak}
-    value = aggregate_throughput(K, ms * 1e-3, 1) * units      # ms is already the max over ranks
+    clocks = ClockSampler(local_rank)
 
-    line = {"metric": "decode tokens/sec (seq_len=1)", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if tp else "weak", "vs_baseline": None,
-            "dtype": "int4 weights, fp16 storage, fp32 accumulate", "data": "synthetic",
-            "config": {"workload": f"Llama-2-{args.model.upper()} w4-g128 random-init .bin, greedy decode -n {K}, batch 1",
-                       "l2": "inputs larger than L2 (3.6 GB of weights per step)", "parallelism": ("tp%d" % world if tp else "replicas x%d" % world) if world > 1 else "1 GPU"},
-            "clocks": clk,
-            "e2e": {"value": (e2e_val * units) if e2e_val else None, "unit": "tokens/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 8,
-                    "how": "lq4_generate_tokens(host prompt ids -> host ids), wall clock of its loop, pipelined launch; per step the kernel "
-                           "reads the token id from pinned host memory and writes the new id and position back to it"},
-            "gpu_launches": K,
-            "roofline": roofline,
-            "roofline_ffn_op": roofline_ffn,
-            "gemv_4096_op": gemv_op}
+    # ---- phase A: one GPU per rank (N = 1: the headline; N > 1: the replicas, and the ids the TP run must reproduce) ----
+    eng = Engine(E, lib, path, cfg, rank, world, False)
+    eng.warm(K, W)
+    clocks.start()
+    ms1, ids1 = eng.timed(K, barrier)
+    ms1 = max_over_ranks(ms1, world)
+    n, secs1, out1 = eng.e2e(K, barrier)
+    assert out1[1:n] == ids1[1:n], "pipelined host API and raw enqueue disagree on token ids"
+    secs1 = max_over_ranks(secs1, world)
+    extras = {}
+    if world == 1 and not args.no_extras:
+        # the op-by-op path (option fused = 0): the reference's op sequence through the per-op wrappers, ~10 launches per layer
+        lib.lq4_set_option(b"fused", 0)
+        eng.enqueue(W)
+        assert lib.lq4_stream_synchronize() == 0
+        Kf = min(K, 64)
+        msf, idsf = eng.timed(Kf, barrier)
+        lib.lq4_set_option(b"fused", 1)
+        extras["fused0"] = {"value": Kf / (msf * 1e-3), "unit": "tokens/s", "ms_per_step": msf / Kf, "steps": Kf, "ids_equal_fused": idsf[1:Kf + 1] == ids1[1:Kf + 1],
+                            "how": "option fused=0: run_llama_network issues the reference's op sequence through the per-op operator wrappers + stand-alone sampler"}
+        extras["roofline_ffn_op"], extras["gemv_4096_op"] = op_timings(eng, lib, E, cfg, peak)
+    eng.close()
+
+    line = {"metric": METRIC, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W, "higher_is_better": True, "vs_baseline": None,
+            "dtype": DTYPE, "data": "synthetic"}
+    workload = f"Llama-2-{args.model.upper()} w4-g128 random-init .bin, greedy decode -n {K}, batch 1"
+    e2e_how = ("lq4_generate_tokens(host prompt ids -> host ids), ns wall clock of its loop, pipelined launch; per step the kernel "
+               "reads the token id from pinned host memory and writes the new id and position back to it")
+    single = {"value": K / (ms1 * 1e-3), "ms_per_step": ms1 / K, "e2e": (n - 1) / secs1}
+    if not tp:
+        value = world * K / (ms1 * 1e-3)
+        line.update({"value": value, "ms_per_step": ms1 / K, "scaling": "weak",
+                     "config": {"workload": workload, "l2": "inputs larger than L2 (3.6 GB of weights per step)",
+                                "parallelism": ("replicas x%d (independent streams, no data-path collective)" % world) if world > 1 else "1 GPU"},
+                     "e2e": {"value": world * (n - 1) / secs1, "unit": "tokens/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 8, "how": e2e_how},
+                     "gpu_launches": K, "roofline": roofline_record(E, cfg, args.model, K, ms1, peak, peak_src)})
+    else:
+        # ---- phase B: ONE stream, tensor parallel over all ranks ----
+        eng = Engine(E, lib, path, cfg, rank, world, True)
+        eng.warm(K, W)
+        ms, ids = eng.timed(K, barrier)
+        ms = max_over_ranks(ms, world)
+        nt, secs, outt = eng.e2e(K, barrier)
+        secs = max_over_ranks(secs, world)
+        same = float(ids[1:K + 1] == ids1[1:K + 1] and outt[1:nt] == ids1[1:nt])
+        same = min_over_ranks(same, world) == 1.0          # every rank's TP ids equal its own one-GPU ids (which are the reference's)
+        eng.close()
+        L = cfg["n_layers"]
+        nx = 4 * L + 1            # cross-GPU hand-overs per token: attention out, o, gate/up, down per layer + the sampler's candidates
+        line.update({"value": K / (ms * 1e-3), "ms_per_step": ms / K, "scaling": "strong",
+                     "config": {"workload": workload, "l2": "inputs larger than L2 (3.6 GB of weights per step, 1/%d per GPU)" % world,
+                                "parallelism": "tp%d (column split of every matrix, activations exchanged by peer stores over NVLink inside the decode kernel)" % world},
+                     "e2e": {"value": (nt - 1) / secs, "unit": "tokens/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 8, "how": e2e_how + " (every rank runs the loop)"},
+                     "gpu_launches": K, "roofline": roofline_record(E, cfg, args.model, K, ms, peak, peak_src, share=world),
+                     "tp": {"ids_match_single_gpu": bool(same), "ids_checked": K, "exchanges_per_token": nx,
+                            "us_per_exchange_est": max(0.0, (ms / K - ms1 / K / world) * 1000.0 / nx),
+                            "us_per_exchange_how": "(TP ms/token - one-GPU ms/token / N) / cross-GPU hand-overs per token: what the exchanges cost beyond an ideal split",
+                            "speedup_vs_single_gpu": (ms1 / K) / (ms / K)},
+                     "single_gpu": {"value": single["value"], "ms_per_step": single["ms_per_step"], "how": "the same ranks, one GPU each, same run (max over ranks)"},
+                     "replicas": {"value": world * K / (ms1 * 1e-3), "unit": "tokens/s", "scaling": "weak",
+                                  "how": "N independent streams, one per GPU, no data-path collective (aggregate over the slowest rank's time)"}})
+        if not same and rank == 0:
+            print("bench.py: tensor-parallel ids differ from the single-GPU ids", file=sys.stderr)
+    line["clocks"] = clocks.stop()
+    line.update(extras)
+
+    if rank == 0 and world == 1 and not args.no_extras and args.model == "7b":
+        # BASELINE.json configs[2]: the 13B model on the same GPU, same measurement
+        try:
+            cfg13 = model_cfg("13b")
+            p13, _ = synth_paths("13b", cfg13)
+            st = os.statvfs(os.path.dirname(p13))
+            if os.path.exists(p13 + ".ok") or st.f_bavail * st.f_frsize > (9 << 30):
+                p13, _ = ensure_files(lib, E, "13b", cfg13, 0)
+                e13 = Engine(E, lib, p13, cfg13, 0, 1, False)
+                e13.warm(K, W)
+                ms13, _ = e13.timed(K, barrier)
+                e13.close()
+                r13 = roofline_record(E, cfg13, "13b", K, ms13, peak, peak_src)
+                line["model_13b"] = {"workload": f"Llama-2-13B w4-g128 random-init .bin, greedy decode -n {K}, batch 1", "value": K / (ms13 * 1e-3),
+                                     "unit": "tokens/s", "ms_per_step": ms13 / K, "roofline": r13}
+            else:
+                line["model_13b"] = {"unavailable": "not enough scratch space for the 7.2 GB file"}
+        except Exception as e:
+            line["model_13b"] = {"unavailable": str(e)[:200]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            line["cpu_baseline"] = cpu_baseline_sample(path, cfg, 1)
+            line["cpu_baseline"] = cpu_port_tokens(path, cfg, 1, 2)
+            line["cpu_baseline_all_threads"] = cpu_port_tokens(path, cfg, os.cpu_count() or 1, 3)
         except Exception as e:  # the oracle is test infrastructure: report, never fall back to it
             line["cpu_baseline"] = {"unavailable": str(e)[:200]}
-    lib.lq4_free_transformer(C.byref(t))
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -70,7 +70,8 @@ typedef struct {
 } Transformer; /* common.h:74-78 */
 #endif /* LQ4_TYPES_H */
 
-/* reference sampler.h:3-13 (same fields, same order) */
+/* reference sampler.h:3-13 (same fields, same order); define LQ4_HAVE_SAMPLER when sampler.h is already included */
+#ifndef LQ4_HAVE_SAMPLER
 typedef struct {
     int vocab_size;
     int* indices;
@@ -82,6 +83,7 @@ typedef struct {
     float topp;
     unsigned long long rng_state;
 } Sampler;
+#endif /* LQ4_HAVE_SAMPLER */
 
 #ifdef __cplusplus
 extern "C" {
@@ -92,6 +94,7 @@ int lq4_init(int device);                 /* select device, create the stream; 0
 void* lq4_get_stream(void);               /* the cudaStream_t everything is enqueued on */
 void lq4_set_stream(void* cuda_stream);   /* adopt a caller-owned stream (e.g. torch's) */
 int lq4_stream_synchronize(void);         /* cudaStreamSynchronize + cudaGetLastError; 0 on success */
+int lq4_stream_query(void);               /* non-blocking: 0 = everything enqueued has finished, 1 = still running, 2 = a CUDA error (see lq4_last_error) */
 const char* lq4_last_error(void);
 int lq4_sm_count(void);
 void lq4_set_option(const char* name, int value); /* "pdl" (0/1), "fused" (0/1), "graphs" (0/1) */
@@ -122,7 +125,13 @@ void lq4_rope_rotation(lq4_half* q, lq4_half* k, int num_heads, int num_kv_heads
 void lq4_multi_head_attention(lq4_half* output, lq4_half* q, lq4_half* key_cache, lq4_half* value_cache,
                               lq4_half* att, int num_heads, int head_size, int kv_mul, int max_seq_len,
                               int* pPos);
-/* run_llama_network, llama2_q4.cu:286-340: one decode step at device position *pPos */
+/* run_llama_network, llama2_q4.cu:286-340: one decode step at device position *pPos.
+ * With the default fused step (option "fused" = 1) the activations travel in a private buffer: after the call ONLY
+ * RunState::logits, the KV-cache rows of this position, RunState::pos / SharedData::pos and SharedData::tokens hold what the
+ * reference leaves there; x, xb, hb, q and att are NOT written (a host that reads them must set option "fused" to 0, which
+ * runs the reference's op sequence through the per-op wrappers above and fills every buffer).  Under tensor parallelism
+ * (lq4_tp_config) this call, lq4_sample, copyLogits and non-greedy sampling exit with an error: only the fused greedy step
+ * (lq4_run_transformer with temperature 0, lq4_enqueue_step, lq4_generate_tokens) is complete on every rank. */
 void lq4_run_llama_network(int* pPos, Config* p, RunState* s, TransformerWeights* w, int seq_len_bin);
 /* run_transformer, llama2_q4.cu:346-395: graph-cached forward + sample.  NOT capture-safe (it captures). */
 void lq4_run_transformer(int gen_token, Config* p, RunState* s, TransformerWeights* w, int copyLogits,

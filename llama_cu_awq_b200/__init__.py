@@ -72,6 +72,7 @@ _SIGNATURES = {
     "lq4_get_stream": (_P, []),
     "lq4_set_stream": (None, [_P]),
     "lq4_stream_synchronize": (C.c_int, []),
+    "lq4_stream_query": (C.c_int, []),
     "lq4_last_error": (C.c_char_p, []),
     "lq4_sm_count": (C.c_int, []),
     "lq4_set_option": (None, [C.c_char_p, C.c_int]),

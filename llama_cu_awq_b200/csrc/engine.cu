@@ -118,7 +118,7 @@ void ensure_init() {
     const char* env;
     if ((env = getenv("LQ4_PDL"))) g.opt_pdl = atoi(env);
     if ((env = getenv("LQ4_FUSED"))) g.opt_fused = atoi(env);
-    if ((env = getenv("LQ4_NWC"))) g.opt_nwc = atoi(env);
+    if ((env = getenv("LQ4_NWC"))) { g.opt_nwc = atoi(env); if (g.opt_nwc != 0 && g.opt_nwc < 8) g.opt_nwc = 8; }
     if ((env = getenv("LQ4_NOMATH"))) g.opt_nomath = atoi(env);
     if ((env = getenv("LQ4_NSLOTS"))) g.opt_nslots = atoi(env);
     if ((env = getenv("LQ4_SLOT_BYTES"))) g.opt_slot_bytes = atoi(env);
@@ -194,10 +194,12 @@ float2* rope_table(float theta, int head_size, int seq_len) {
     return tab;
 }
 
-long time_in_ms() {   // llama2_q4.cu:400-405
-    struct timespec time;
-    timespec_get(&time, TIME_UTC);
-    return time.tv_sec * 1000 + time.tv_nsec / 1000000;
+// wall clock of the host loops in ns (the reference's time_in_ms, llama2_q4.cu:400-405, rounds to 1 ms: too coarse for a
+// 20-step run of 2 ms steps)
+long long time_in_ns() {
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return (long long)t.tv_sec * 1000000000ll + t.tv_nsec;
 }
 
 // ------------------------------------------------------------------------------- persistent kernel: plans and ops
@@ -370,7 +372,9 @@ void run_single(Op& op, const int* pPos) {
     } else {
         grid = 1;
     }
-    if (!make_plan(pl, default_nwc(), xs, meta, 0)) unsupported();      // a single op only ever uses buffer 0
+    // the attention op keeps four PV chains per warp (tx = warp + k * nwc, k < 4): it needs at least 8 consumer warps
+    const int nwc = (op.kind == OP_ATTN) ? std::max(default_nwc(), 8) : default_nwc();
+    if (!make_plan(pl, nwc, xs, meta, 0)) unsupported();      // a single op only ever uses buffer 0
     if (op.kind <= OP_CLS && !op_set_chunking(op, pl.ring_bytes)) unsupported();
     launch_interp(pl, nullptr, 1, &op, pPos, -1, false, grid);
 }
@@ -459,6 +463,14 @@ int lq4_stream_synchronize(void) {
     if (e != cudaSuccess) { set_err("stream synchronize", e); return 1; }
     return 0;
 }
+int lq4_stream_query(void) {
+    ensure_init();
+    cudaError_t e = cudaStreamQuery(g.stream);
+    if (e == cudaSuccess) return 0;
+    if (e == cudaErrorNotReady) return 1;
+    set_err("stream query", e);
+    return 2;
+}
 const char* lq4_last_error(void) { return g.err; }
 int lq4_sm_count(void) { ensure_init(); return g.sm_count; }
 
@@ -471,7 +483,10 @@ void lq4_set_option(const char* name, int value) {
     ensure_init();
     if (!strcmp(name, "pdl")) g.opt_pdl = value;
     else if (!strcmp(name, "fused")) g.opt_fused = value;
-    else if (!strcmp(name, "nwc")) { g.opt_nwc = value; cudaStreamSynchronize(g.stream); drop_net_plans(); }
+    else if (!strcmp(name, "nwc")) {
+        if (value != 0 && value < 8) { fprintf(stderr, "lq4: nwc must be 0 (default) or >= 8 (RMSNorm staging and the attention op need 8 consumer warps); ignored\n"); return; }
+        g.opt_nwc = value; cudaStreamSynchronize(g.stream); drop_net_plans();
+    }
     else if (!strcmp(name, "slot_bytes")) { g.opt_slot_bytes = value; cudaStreamSynchronize(g.stream); drop_net_plans(); }
     else if (!strcmp(name, "nslots")) { g.opt_nslots = value; cudaStreamSynchronize(g.stream); drop_net_plans(); }
     else if (!strcmp(name, "trace")) g.opt_trace = value;
@@ -826,8 +841,19 @@ static bool run_network_fused(int* pPos, Config* p, RunState* s, TransformerWeig
     return true;
 }
 
+// Tensor parallel: only the fused greedy step is complete on every rank.  Its classifier writes this rank's vocabulary slice
+// of the logits only, and its sampler is the launch's one cross-rank rendezvous (every rank has finished polling the
+// activation buffers before any rank leaves it).  Anything that needs the full logits on one rank -- temperature / top-p
+// sampling, perplexity (copyLogits), run_llama_network on its own, lq4_step with a logits buffer -- is refused, loudly.
+[[noreturn]] static void tp_unsupported(const char* what) {
+    fprintf(stderr, "lq4: %s is not available under tensor parallelism (rank %d of %d): only the fused greedy decode step is; "
+                    "run it on one GPU\n", what, g.tp_rank, g.tp_world);
+    exit(EXIT_FAILURE);
+}
+
 void lq4_run_llama_network(int* pPos, Config* p, RunState* s, TransformerWeights* w, int seq_len_bin) {
     ensure_init();
+    if (g.tp_world > 1) tp_unsupported("run_llama_network without the fused sampler");
     if (g.opt_fused && run_network_fused(pPos, p, s, w, false, -1)) return;
     run_network_unfused(pPos, p, s, w, seq_len_bin);
 }
@@ -886,6 +912,7 @@ static void sample_nongreedy(Sampler* sampler, RunState* s, float coin, cudaStre
 
 void lq4_sample(Sampler* sampler, RunState* s, int gen_token, void* cuda_stream) {
     ensure_init();
+    if (g.tp_world > 1) tp_unsupported("sample() on the full logits");
     const float coin = random_f32(&sampler->rng_state);   // one draw per step, greedy or not (sampler.h:45)
     if (is_greedy(sampler, gen_token)) {
         argmax_kernel<<<1, 1024, 0, (cudaStream_t)cuda_stream>>>(s->logits, sampler->vocab_size, &(s->shared_data->tokens[0]),
@@ -904,6 +931,7 @@ static void forward_and_sample(int gen_token, Config* p, RunState* s, Transforme
             return;
         }
     }
+    if (g.tp_world > 1) tp_unsupported(copyLogits ? "perplexity mode (copyLogits)" : is_greedy(pSampler, gen_token) ? "the op-by-op path (fused=0 or an unsupported shape)" : "temperature / top-p sampling");
     lq4_run_llama_network(s->pos, p, s, w, seq_len_bin);
     if (copyLogits) {                                  // llama2_q4.cu:377-382 (perplexity mode)
         float* pOutput = s->logits_array + (size_t)p->vocab_size * s->shared_data->pos;
@@ -1061,6 +1089,7 @@ void lq4_reset(Transformer* t, const int* tokens, int n) {   // llama2_q4.cu:461
 
 int lq4_step(Transformer* t, Sampler* sampler, int gen_token, half* logits_out, int* next_token_out) {
     ensure_init();
+    if (g.tp_world > 1 && logits_out) tp_unsupported("lq4_step with a logits buffer");
     LQ4_CHECK(cudaStreamSynchronize(g.stream));
     lq4_run_transformer(gen_token, &t->config, &t->state, &t->weights, 0, sampler);
     LQ4_CHECK(cudaStreamSynchronize(g.stream));
@@ -1085,7 +1114,7 @@ int lq4_generate_tokens(Transformer* t, Sampler* sampler, const int* prompt_toke
     if (steps <= 0 || steps > t->config.seq_len) steps = t->config.seq_len;   // llama2_q4.cu:690
     Config* p = &t->config;
     RunState* s = &t->state;
-    const long start = time_in_ms();
+    const long long start = time_in_ns();
     LQ4_CHECK(cudaMemsetAsync(s->pos, 0, sizeof(int), g.stream));
     LQ4_CHECK(cudaStreamSynchronize(g.stream));
     s->shared_data->pos = 0;
@@ -1134,8 +1163,8 @@ int lq4_generate_tokens(Transformer* t, Sampler* sampler, const int* prompt_toke
         cudaEventDestroy(ev[1]);
     }
     LQ4_CHECK(cudaStreamSynchronize(g.stream));
-    const long end = time_in_ms();
-    if (seconds) *seconds = (end - start) / 1000.0;
+    const long long end = time_in_ns();
+    if (seconds) *seconds = (double)(end - start) * 1e-9;
     return pos;
 }
 

@@ -131,6 +131,21 @@ long time_in_ms() {   // llama2_q4.cu:400-405
     exit(EXIT_FAILURE);
 }
 
+// Spin on the pinned doorbell the device-side sampler writes (SharedData::pos).  The spin is bounded: every so often the
+// stream is queried, so that a launch that died (a CUDA error, or the kernel's own protocol time-out trap) ends the program
+// with the error instead of hanging it; the reference's cudaStreamSynchronize loop (llama2_q4.cu:468) would return likewise.
+void wait_doorbell(SharedData* sd, int pos) {
+    for (unsigned spins = 0; sd->pos < pos; spins++) {
+        if ((spins & 0xFFFFu) != 0xFFFFu) continue;
+        const int q = lq4_stream_query();
+        if (q == 2 || (q == 0 && sd->pos < pos)) {
+            fprintf(stderr, "\nlq4: the decode step for position %d never published its token: %s\n", pos,
+                    q == 2 ? lq4_last_error() : "the stream is idle");
+            exit(EXIT_FAILURE);
+        }
+    }
+}
+
 void generate(Transformer* t, Tokenizer* tok, Sampler* sampler, const char* prompt, int steps) {
     if (prompt == nullptr) prompt = "";
     printf("\nEncoding Prompt... ");
@@ -144,6 +159,10 @@ void generate(Transformer* t, Tokenizer* tok, Sampler* sampler, const char* prom
     const int vocab = t->config.vocab_size;
     SharedData* sd = t->state.shared_data;
 
+    // LQ4_DUMP_IDS=<file>: also write the id at every sequence position (parity tooling: ids without parsing the text)
+    const char* dump_path = getenv("LQ4_DUMP_IDS");
+    std::vector<int> ids(1, prompt_tokens[0]);
+
     const long start = time_in_ms();
     int token = prompt_tokens[0], pos = 0, launched = 0;
     lq4_reset(t, prompt_tokens.data(), n_prompt);
@@ -154,7 +173,7 @@ void generate(Transformer* t, Tokenizer* tok, Sampler* sampler, const char* prom
                 lq4_enqueue_step(t, sampler, launched + 1, launched >= n_prompt - 1);
                 launched++;
             }
-            if (pos > 0) while (sd->pos < pos) { /* spin on the pinned doorbell the sampler writes */ }
+            if (pos > 0) wait_doorbell(sd, pos);
         } else {
             lq4_stream_synchronize();
             lq4_run_transformer(pos >= n_prompt - 1, &t->config, &t->state, &t->weights, 0, sampler);
@@ -163,6 +182,7 @@ void generate(Transformer* t, Tokenizer* tok, Sampler* sampler, const char* prom
             int next = sd->tokens[pos];
             if (next >= vocab) next = 0;
             tok->print_piece(token, next);
+            ids.push_back(next);
             if (next == kEos) break;
             token = next;
         }
@@ -174,6 +194,13 @@ void generate(Transformer* t, Tokenizer* tok, Sampler* sampler, const char* prom
     const double secs = (end - start) / 1000.0;
     const int timed_tokens = pos - 1;
     printf("\nachieved tok/s: %f. Tokens: %d, seconds: %g\n", timed_tokens / secs, timed_tokens, secs);
+    if (dump_path != nullptr) {
+        if (FILE* f = fopen(dump_path, "w")) {
+            fprintf(f, "%d\n", n_prompt);
+            for (int id : ids) fprintf(f, "%d\n", id);
+            fclose(f);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------- chat mode (llama2_q4.cu:494-601)

@@ -102,6 +102,29 @@ int ref_step(int gen_token, half* logits_out, int* next_token_out) {
     if (next_token_out) *next_token_out = g_ref_t.state.shared_data->tokens[pos];
     return pos;
 }
+// Steady-state timing of the stock loop body (llama2_q4.cu:465-470: cudaStreamSynchronize, then run_transformer) for `steps`
+// positions from the current one, with CUDA events on the reference's own stream.  Call it after a pass over the same
+// positions, so that every length bin's graph is already captured (llama2_q4.cu:362-371).  Returns milliseconds.
+float ref_time_steps(int steps, int gen_from) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaStreamSynchronize(stream);
+    cudaEventRecord(e0, stream);
+    for (int i = 0; i < steps; i++) {
+        cudaStreamSynchronize(stream);
+        run_transformer(i >= gen_from, &g_ref_t.config, &g_ref_t.state, &g_ref_t.weights, false, &g_ref_sampler);
+    }
+    cudaEventRecord(e1, stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return ms;
+}
+// token at sequence position i (pinned SharedData::tokens), after the stream has been synchronised
+int ref_token_at(int i) { cudaStreamSynchronize(stream); return g_ref_t.state.shared_data->tokens[i]; }
 // device pointers of the reference run state, for bit-compares of intermediates
 void* ref_state_ptr(int which) {
     RunState* s = &g_ref_t.state;

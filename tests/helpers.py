@@ -131,8 +131,9 @@ def ref():
     """oracle/_ref/libq4ref.so: the UNMODIFIED reference TU behind a C shim (oracle/ref_harness.cu)."""
     global _ref
     if _ref is None:
-        if not os.path.exists(REF_SO):
-            return None
+        # The GPU parity tests are reference comparisons: on a GPU box a missing reference build is a FAILURE, never a
+        # silent pass (oracle/build_ref.sh builds it wherever /root/reference exists; the built files travel with the snapshot).
+        assert os.path.exists(REF_SO), f"{REF_SO} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` where /root/reference exists"
         r = C.CDLL(REF_SO)
         P = C.c_void_p
         r.ref_rmsnorm.argtypes = [P, P, P, C.c_int]
@@ -151,10 +152,20 @@ def ref():
         r.ref_step.argtypes = [C.c_int, P, P]
         r.ref_state_ptr.restype = C.c_void_p
         r.ref_state_ptr.argtypes = [C.c_int]
+        r.ref_time_steps.restype = C.c_float
+        r.ref_time_steps.argtypes = [C.c_int, C.c_int]
+        r.ref_token_at.restype = C.c_int
+        r.ref_token_at.argtypes = [C.c_int]
         r.ref_close.argtypes = []
         r.ref_last_cuda_error.restype = C.c_int
         _ref = r
     return _ref
+
+
+def require_ref_bin():
+    """oracle/_ref/llama2_q4_ref (the stock reference program): required by the GPU CLI / transcript tests."""
+    assert os.path.exists(REF_BIN), f"{REF_BIN} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` where /root/reference exists"
+    return REF_BIN
 
 
 # ------------------------------------------------------------------ torch device helpers (GPU only)

@@ -19,19 +19,25 @@ def _ngpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("cfg_name,world", [("TINY", 2), ("SMALL", 2), ("TINY_GQA", 2), ("SMALL", 4), ("SMALL", 8)])
+@pytest.mark.parametrize("cfg_name,world", [("TINY", 2), ("SMALL", 2), ("TINY_GQA", 2), ("7B", 2), ("SMALL", 4), ("7B", 4), ("SMALL", 8), ("7B", 8)])
 def test_tp_tokens_equal_single_gpu(cfg_name, world):
     if _ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
     import llama_cu_awq_b200 as E
     lib = E.lib()
     assert lib.lq4_init(0) == 0
-    cfg = getattr(H, cfg_name)
+    full = cfg_name == "7B"                 # BASELINE.json configs[3]: the 7B model itself, sharded
+    cfg = E.LLAMA2_7B if full else getattr(H, cfg_name)
     steps, prompt = 48, [1, 35, 72]
     with tempfile.TemporaryDirectory() as d:
         path, outp = os.path.join(d, "m.bin"), os.path.join(d, "tp.json")
         c = E.Config(**cfg)
-        assert lib.lq4_write_synth_model(path.encode(), C.byref(c), 2025) == os.path.getsize(path)
+        if full:
+            sys.path.insert(0, H.ROOT)
+            import bench as B
+            path, _ = B.ensure_files(lib, E, "7b", cfg)
+        else:
+            assert lib.lq4_write_synth_model(path.encode(), C.byref(c), 2025) == os.path.getsize(path)
         # single GPU
         t = E.Transformer()
         assert lib.lq4_build_transformer(C.byref(t), path.encode(), 0) == 0
@@ -52,3 +58,17 @@ def test_tp_tokens_equal_single_gpu(cfg_name, world):
         res = json.load(open(outp))
         assert res["all_equal"], "ranks disagree on the token ids"
         assert res["tokens"] == single, f"TP={world} ids differ from single GPU"
+
+
+def test_tp_refuses_what_it_cannot_do():
+    """Under tensor parallelism only the fused greedy step is complete on every rank (each classifier writes its own
+    vocabulary slice): anything that needs the full logits must exit with an error, not run on stale data."""
+    code = (
+        "import ctypes as C, sys, os, tempfile; sys.path.insert(0, %r); sys.path.insert(0, %r); import helpers as H; import llama_cu_awq_b200 as E;"
+        "lib = E.lib(); lib.lq4_init(0); lib.lq4_tp_config(0, 2); d = tempfile.mkdtemp(); p = os.path.join(d, 'm.bin');"
+        "c = E.Config(**H.TINY); lib.lq4_write_synth_model(p.encode(), C.byref(c), 1); t = E.Transformer();"
+        "lib.lq4_build_transformer(C.byref(t), p.encode(), 0); s = E.Sampler(); lib.lq4_build_sampler(C.byref(s), 512, 0.8, 0.9, 1);"
+        "tok = (C.c_int * 1)(1); lib.lq4_reset(C.byref(t), tok, 1); lib.lq4_enqueue_step(C.byref(t), C.byref(s), 1, 1); print('survived')"
+        % (H.ROOT, os.path.join(H.ROOT, "tests")))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "not available under tensor parallelism" in r.stderr and "survived" not in r.stdout
