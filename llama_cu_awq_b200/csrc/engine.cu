@@ -611,13 +611,11 @@ void lq4_rope_rotation(half* q, half* k, int num_heads, int num_kv_heads, int he
 static void fill_attn_op(Op& op, half* output, half* q, half* key_cache, half* value_cache, half* att, int num_heads,
                          int head_size, int kv_mul, int max_seq_len) {
     if (head_size != 32 && head_size != 64 && head_size != 128) unsupported();
-    if (max_seq_len > MAX_SEQ_LEN_SMEM_KERNEL) {
-        // the reference switches to softmax_kernel_no_smem here (llama2_q4.cu:276-279), whose fp16
-        // rounding of exp() differs; that variant is scope row f2 and not built yet.
-        fprintf(stderr, "lq4: sequence bins above %d are not supported yet\n", MAX_SEQ_LEN_SMEM_KERNEL);
-        exit(EXIT_FAILURE);
-    }
     op.kind = OP_ATTN;
+    // MultiHeadAttention picks the softmax kernel by its max_seq_len argument (llama2_q4.cu:276-279): beyond 8192 it is
+    // softmax_kernel_no_smem, whose exp() values are rounded to fp16 before the division.  The fused step overrides this with
+    // the position-dependent rule the reference's graph bins amount to (see get_net_plan).
+    op.exp16_from = (max_seq_len > MAX_SEQ_LEN_SMEM_KERNEL) ? 0 : 0x7fffffff;
     op.q = q; op.kcache = key_cache; op.vcache = value_cache; op.att_out = att; op.attn_out = output;
     op.n_heads = num_heads; op.head_size = head_size; op.kv_mul = kv_mul;
     op.kv_stride = (num_heads * head_size) / kv_mul;
@@ -628,13 +626,13 @@ static void fill_attn_op(Op& op, half* output, half* q, half* key_cache, half* v
 void lq4_multi_head_attention(half* output, half* q, half* key_cache, half* value_cache, half* att, int num_heads,
                               int head_size, int kv_mul, int max_seq_len, int* pPos) {
     ensure_init();
-    if (head_size != 32 && head_size != 64 && head_size != 128 && head_size % 32 == 0 && head_size <= 256 &&
-        max_seq_len <= MAX_SEQ_LEN_SMEM_KERNEL) {
+    if (head_size != 32 && head_size != 64 && head_size != 128 && head_size % 32 == 0 && head_size <= 256) {
         // other head sizes: the stand-alone kernel (same arithmetic, one block of 1024 threads per head)
         AttnParams ap = {};
         ap.out = output; ap.q = q; ap.kcache = key_cache; ap.vcache = value_cache; ap.att_out = att;
         ap.head_size = head_size; ap.kv_mul = kv_mul; ap.kv_stride = (num_heads * head_size) / kv_mul;
         ap.pPos = pPos; ap.alpha = (float)(1.0 / sqrt((double)head_size)); ap.max_seq = max_seq_len;
+        ap.exp16 = max_seq_len > MAX_SEQ_LEN_SMEM_KERNEL;
         const size_t smem = sizeof(float) * (size_t)(head_size + 32 + 4 + ((max_seq_len + 3) & ~3) + 32 * head_size);
         allow_smem(attention_kernel, smem);
         launch(attention_kernel, dim3(num_heads), dim3(kAttnThreads), smem, false, ap);
@@ -699,7 +697,7 @@ static NetPlan& get_net_plan(Config* p, RunState* s, TransformerWeights* w) {
     const int head_size = dim / p->n_heads;
     const int kv_dim = (p->dim * p->n_kv_heads) / p->n_heads;
     const int kv_mul = p->n_heads / p->n_kv_heads;
-    if ((head_size != 32 && head_size != 64 && head_size != 128) || p->seq_len > MAX_SEQ_LEN_SMEM_KERNEL) return np;
+    if (head_size != 32 && head_size != 64 && head_size != 128) return np;
     if (dim > 1024 * kNormMaxT || dim % 64) return np;      // fused RMSNorm staging (interp_sm100.cuh, stage_norm)
     // Tensor parallel (T ranks, one process per GPU): every matrix is split by output columns, rank r owning the r-th
     // contiguous slice (heads r*H/T.. for q|k|v and attention, hidden and dim slices for the FFN and the projections, vocabulary
@@ -755,6 +753,9 @@ static NetPlan& get_net_plan(Config* p, RunState* s, TransformerWeights* w) {
             fill_attn_op(op, nullptr, s->q, s->key_cache + loff + R * skv, s->value_cache + loff + R * skv, nullptr, sheads, head_size, kv_mul,
                          p->seq_len);
             op.kv_stride = kv_dim;
+            // run_transformer's graph bins (llama2_q4.cu:354-360) hand MultiHeadAttention a max_seq_len above 8192 exactly when
+            // pos + 1 > 8192 (bins are 128 ... 8192, then the model's seq_len): the softmax variant depends on the position only
+            op.exp16_from = MAX_SEQ_LEN_SMEM_KERNEL;
             op.qt = qt + R * sdim; op.krawt = krawt + R * skv; op.vrawt = vrawt + R * skv;
             op.attn_out32 = xbt + R * sdim; op.attn_bcast = bc; op.rope_tab = rope_tab;
             ops.push_back(op);
@@ -922,9 +923,19 @@ void lq4_sample(Sampler* sampler, RunState* s, int gen_token, void* cuda_stream)
     }
 }
 
-// forward + sample; seq_len_bin only matters to the op-by-op path
+// run_transformer's length bin for a sequence of seq_len positions (llama2_q4.cu:354-360): 128, 256, ... 8192, else the model's
+// seq_len.  It sizes the QK grid there; here it only selects the softmax variant of the op-by-op path (bins above 8192).
+static int seq_len_bin_of(const Config* p, int seq_len) {
+    int bin = 128;
+    for (int i = 0; i < 7; i++, bin *= 2)
+        if (seq_len <= bin) return bin;
+    return p->seq_len;
+}
+
+// forward + sample; seq_len (= pos + 1) only matters to the op-by-op path
 static void forward_and_sample(int gen_token, Config* p, RunState* s, TransformerWeights* w, int copyLogits,
-                               Sampler* pSampler, int seq_len_bin) {
+                               Sampler* pSampler, int seq_len) {
+    const int seq_len_bin = seq_len_bin_of(p, seq_len);
     if (g.opt_fused && !copyLogits && is_greedy(pSampler, gen_token)) {
         if (run_network_fused(s->pos, p, s, w, true, gen_token != 0)) {      // greedy sampler = last op of the persistent kernel
             (void)random_u32(&pSampler->rng_state);
@@ -945,7 +956,7 @@ void lq4_run_transformer(int gen_token, Config* p, RunState* s, TransformerWeigh
     ensure_init();
     // the reference picks a CUDA graph by length bin here (llama2_q4.cu:354-372); this engine's step is a
     // single launch whose work depends only on the device-side position, so there is nothing to select
-    forward_and_sample(gen_token, p, s, w, copyLogits, pSampler, p->seq_len);
+    forward_and_sample(gen_token, p, s, w, copyLogits, pSampler, s->shared_data->pos + 1);   // the host copy of the position, like the reference (:354)
 }
 
 // ---------------------------------------------------------------------------------- loader

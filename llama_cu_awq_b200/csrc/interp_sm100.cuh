@@ -102,6 +102,7 @@ struct Op {
     int attn_bcast;        // tensor parallel: broadcast attn_out32 to every rank
     const float2* rope_tab;
     int n_heads, head_size, kv_mul, kv_stride, max_seq;
+    int exp16_from;        // softmax over more than this many positions uses the arithmetic of softmax_kernel_no_smem (gpu_kernels.h:403-446)
     float att_alpha;
     // OP_ARGMAX
     const half* logits;
@@ -902,6 +903,8 @@ __device__ void run_q4(Ctx& c, const Op& op) {
         val_mark(c, 8, producer_issued(c)); val_mark(c, 10, c.qtotal); val_mark(c, 11, smid);
     }
 
+    // (Waiting for the first task's weights BEFORE the staging was measured and dropped: at a ring-epoch change the producer is
+    // still draining, and the polls of the hand-over then start late: 1.91 -> 2.05 ms per 7B token.)
     mbar_wait(c.sm.mfull(mb), (c.mcount >> 1) & 1);      // scales / zero points of this op have landed
     cyc_mark(c, 4);
 #pragma unroll 1
@@ -1227,7 +1230,10 @@ __device__ void run_attn_t(Ctx& c, const Op& op, bool prefetched) {
         for (int ti = 0; ti < kAttnAhead; ti++) attn_tile_async(c, vbase, op.kv_stride, hs, op.max_seq, ti, pos);
         named_bar(kBarAll, nt);
         trace_mark(c, 3);
-        // ---- softmax (idle reference threads seed the max with 0, gpu_kernels.h:374) ----
+        // ---- softmax (idle reference threads seed the max with 0, gpu_kernels.h:374).  Beyond 8192 positions the reference
+        // switches to softmax_kernel_no_smem (llama2_q4.cu:276-279, gpu_kernels.h:403-446), which keeps exp() in the fp16 score
+        // buffer: the sum still adds the unrounded values, but the quotient is formed from the fp16-rounded one. ----
+        const bool exp16 = size > op.exp16_from;
         float mx = (size < 1024) ? 0.0f : -INFINITY;
         for (int i = tid; i < size; i += nt) mx = fmaxf(mx, att[i]);
         mx = warp_max(mx);
@@ -1240,7 +1246,7 @@ __device__ void run_attn_t(Ctx& c, const Op& op, bool prefetched) {
             float ssum = 0.0f;
             for (int i = vt; i < size; i += 1024) {
                 const float e = expf(__fsub_rn(att[i], mx));
-                att[i] = e;
+                att[i] = exp16 ? __half2float(__float2half_rn(e)) : e;
                 ssum = __fadd_rn(ssum, e);
             }
             ssum = warp_tree_sum(ssum);

@@ -630,6 +630,7 @@ struct AttnParams {
     const int* pPos;
     float alpha;             // (float)(1.0 / sqrt((double)head_size)), llama2_q4.cu:273
     int max_seq;             // capacity of the score buffer in shared memory
+    int exp16;               // 1: arithmetic of softmax_kernel_no_smem (gpu_kernels.h:403-446), the reference's choice when max_seq_len > 8192
 };
 
 constexpr int kAttnThreads = 1024;
@@ -682,7 +683,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const AttnPa
     float ssum = 0.0f;
     for (int i = tid; i < size; i += kAttnThreads) {
         const float e = expf(__fsub_rn(att[i], mx));
-        att[i] = e;
+        att[i] = p.exp16 ? __half2float(__float2half_rn(e)) : e;   // no_smem variant: exp() is parked in the fp16 score buffer
         ssum = __fadd_rn(ssum, e);                     // FMUL (expf tail) + FADD in the reference SASS: not fused
     }
     ssum = warp_tree_sum(ssum);

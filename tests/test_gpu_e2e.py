@@ -190,3 +190,39 @@ def test_sampling_matches_reference(eng, temperature, topp):
             r.ref_close()
             lib.lq4_destroy_sampler(C.byref(s))
             lib.lq4_free_transformer(C.byref(t))
+
+
+def test_long_context_fused_equals_op_by_op(eng):
+    """Scope row f2, end to end: beyond 8192 positions the reference's graph bin is the model's seq_len, so its attention
+    runs softmax_kernel_no_smem (llama2_q4.cu:354-360, 276-279).  The fused step switches arithmetic by position, the
+    op-by-op path by the bin it computes like run_transformer; both must agree id for id across the switch and well past
+    it (the op-level kernels are bit-exact against the reference in test_gpu_ops.py::test_multi_head_attention_long_context;
+    the reference itself cannot run this model: its `att` buffer holds n_heads*dim scores, llama2_q4.cu:44)."""
+    E, lib = eng
+    cfg = dict(dim=256, hidden_dim=512, n_layers=2, n_heads=4, n_kv_heads=4, vocab_size=512, seq_len=8448, rope_theta=10000.0)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "m.bin")
+        write_model(E, lib, cfg, 31, path)
+        t, s = open_mine(E, lib, path)
+        try:
+            steps = 8400
+            prompt = (C.c_int * 3)(1, 35, 72)
+            outs, last = [], []
+            for fused in (1, 0):
+                lib.lq4_set_option(b"fused", fused)
+                out = (C.c_int * steps)()
+                secs = C.c_double(0)
+                n = lib.lq4_generate_tokens(C.byref(t), C.byref(s), prompt, 3, steps, out, C.byref(secs), 1)
+                assert n == steps
+                outs.append(list(out))
+                lg = np.zeros(cfg["vocab_size"], np.uint16)
+                nxt = C.c_int(0)
+                lib.lq4_step(C.byref(t), C.byref(s), 1, lg.ctypes.data_as(C.c_void_p), C.byref(nxt))      # position 8400
+                last.append(lg)
+            lib.lq4_set_option(b"fused", 1)
+            bad = [i for i, (a, b) in enumerate(zip(outs[0], outs[1])) if a != b]
+            assert not bad, f"fused and op-by-op ids part ways at position {bad[0]}"
+            assert (last[0] == last[1]).all(), "logits at position 8400 differ between the fused and the op-by-op path"
+            assert len(set(outs[0][8200:])) > 8, "the long run should not have collapsed to a fixed point"
+        finally:
+            lib.lq4_free_transformer(C.byref(t))

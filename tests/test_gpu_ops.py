@@ -274,3 +274,36 @@ def test_multi_head_attention(eng, nh, hs, kv_mul, pos):
         assert (H.dev_u16(rout) == got).all(), "attention output must be bit-identical to the reference kernels"
         n = nh * (pos + 1)
         assert (H.dev_u16(ratt)[:n] == H.dev_u16(datt)[:n]).all(), "softmax probabilities must be bit-identical"
+
+
+@pytest.mark.parametrize("nh,hs,kv_mul", [(4, 64, 1), (8, 128, 2), (4, 96, 1)])
+@pytest.mark.parametrize("pos", [100, 1500, 8191, 8192, 9000, 12287])
+def test_multi_head_attention_long_context(eng, nh, hs, kv_mul, pos):
+    """Scope row f2: sequence bins above 8192.  MultiHeadAttention then runs softmax_kernel_no_smem (llama2_q4.cu:276-279,
+    gpu_kernels.h:403-446), which keeps exp() in the fp16 score buffer: the sum adds the unrounded values while the quotient is
+    formed from the rounded one.  Bit-exact against the reference kernels (output and probabilities); hs = 96 takes the
+    stand-alone attention kernel, the others the persistent kernel's attention op."""
+    import torch
+    E, lib = eng
+    r = H.ref()
+    rng = np.random.default_rng(nh * 1000 + hs + pos)
+    seq = 12288
+    kv_dim = nh * hs // kv_mul
+    q = rng.standard_normal(nh * hs).astype(np.float16)
+    kc = (0.5 * rng.standard_normal((seq, kv_dim))).astype(np.float16)
+    vc = rng.standard_normal((seq, kv_dim)).astype(np.float16)
+    dq, dk, dv = H.to_dev(q.view(np.uint16)), H.to_dev(kc.view(np.uint16)), H.to_dev(vc.view(np.uint16))
+    datt = H.to_dev(np.zeros(nh * seq, np.uint16))
+    dout = H.to_dev(np.zeros(nh * hs, np.uint16))
+    dp = dev_pos(pos)
+    lib.lq4_multi_head_attention(dout.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), datt.data_ptr(), nh, hs,
+                                 kv_mul, seq, dp.data_ptr())
+    sync(lib)
+    got = H.dev_u16(dout)
+    ratt = H.to_dev(np.zeros(nh * seq, np.uint16))
+    rout = H.to_dev(np.zeros(nh * hs, np.uint16))
+    r.ref_mha(rout.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), ratt.data_ptr(), nh, hs, kv_mul, seq, dp.data_ptr())
+    torch.cuda.synchronize()
+    assert (H.dev_u16(rout) == got).all(), "attention output must be bit-identical to the reference kernels"
+    n = nh * (pos + 1)
+    assert (H.dev_u16(ratt)[:n] == H.dev_u16(datt)[:n]).all(), "softmax probabilities must be bit-identical"

@@ -1,0 +1,187 @@
+// tools/ubench_trip.cu -- development aid: the INT4 trip loop of interp_sm100.cuh (q4_trip2 + col_meta) alone, fed from
+// shared memory that is filled once, at the production launch geometry (one CTA of 12 warps per SM, 168 registers).  Prints
+// cycles per warp-trip and weights per clock per SM for 1..11 active consumer warps and for alternative trip bodies.
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o build/ubench_trip tools/ubench_trip.cu
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+#include "../llama_cu_awq_b200/csrc/interp_sm100.cuh"
+
+using namespace lq4;
+
+// ---- variant 1: the x pairs of a whole quarter-trip (qi) are loaded before its arithmetic starts ----
+__device__ __forceinline__ void q4_trip2_v1(unsigned long long& acc0, unsigned long long& acc1, uint32_t xaddr, uint32_t w0, uint32_t w1,
+                                            const ColMeta& m0, const ColMeta& m1) {
+    const uint4 wa0 = lds_v4(w0), wb0 = lds_v4(w0 ^ 16), wa1 = lds_v4(w1), wb1 = lds_v4(w1 ^ 16);
+    unsigned long long xp[2][8];
+#pragma unroll
+    for (int e2 = 0; e2 < 4; e2++) lds_v2_b64(xaddr + e2 * kRowBytes, xp[0][2 * e2], xp[0][2 * e2 + 1]);
+#pragma unroll
+    for (int qi = 0; qi < 4; qi++) {
+        if (qi < 3) {
+#pragma unroll
+            for (int e2 = 0; e2 < 4; e2++) lds_v2_b64(xaddr + ((qi + 1) * 4 + e2) * kRowBytes, xp[(qi + 1) & 1][2 * e2], xp[(qi + 1) & 1][2 * e2 + 1]);
+        }
+        float da0[8], db0[8], da1[8], db1[8];
+        dequant8(da0, word_of(wa0, qi), m0.s16, m0.nlo, m0.nhi);
+        dequant8(db0, word_of(wb0, qi), m0.s16, m0.nlo, m0.nhi);
+        dequant8(da1, word_of(wa1, qi), m1.s16, m1.nlo, m1.nhi);
+        dequant8(db1, word_of(wb1, qi), m1.s16, m1.nlo, m1.nhi);
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            ffma2_pk(acc0, da0[e], db0[e], xp[qi & 1][e]);
+            ffma2_pk(acc1, da1[e], db1[e], xp[qi & 1][e]);
+        }
+    }
+}
+
+// ---- variant 2: plain FFMA on four separate chains instead of FFMA2 ----
+__device__ __forceinline__ void q4_trip2_v2(unsigned long long& acc0, unsigned long long& acc1, uint32_t xaddr, uint32_t w0, uint32_t w1,
+                                            const ColMeta& m0, const ColMeta& m1) {
+    const uint4 wa0 = lds_v4(w0), wb0 = lds_v4(w0 ^ 16), wa1 = lds_v4(w1), wb1 = lds_v4(w1 ^ 16);
+    float a0, b0, a1, b1;
+    unpack_f2(acc0, a0, b0); unpack_f2(acc1, a1, b1);
+#pragma unroll
+    for (int qi = 0; qi < 4; qi++) {
+        float da0[8], db0[8], da1[8], db1[8];
+        dequant8(da0, word_of(wa0, qi), m0.s16, m0.nlo, m0.nhi);
+        dequant8(db0, word_of(wb0, qi), m0.s16, m0.nlo, m0.nhi);
+        dequant8(da1, word_of(wa1, qi), m1.s16, m1.nlo, m1.nhi);
+        dequant8(db1, word_of(wb1, qi), m1.s16, m1.nlo, m1.nhi);
+#pragma unroll
+        for (int e2 = 0; e2 < 4; e2++) {
+            unsigned long long xp0, xp1;
+            lds_v2_b64(xaddr + (qi * 4 + e2) * kRowBytes, xp0, xp1);
+            float xa0, xb0, xa1, xb1;
+            unpack_f2(xp0, xa0, xb0); unpack_f2(xp1, xa1, xb1);
+            a0 = __fmaf_rn(da0[2 * e2], xa0, a0); b0 = __fmaf_rn(db0[2 * e2], xb0, b0);
+            a1 = __fmaf_rn(da1[2 * e2], xa0, a1); b1 = __fmaf_rn(db1[2 * e2], xb0, b1);
+            a0 = __fmaf_rn(da0[2 * e2 + 1], xa1, a0); b0 = __fmaf_rn(db0[2 * e2 + 1], xb1, b0);
+            a1 = __fmaf_rn(da1[2 * e2 + 1], xa1, a1); b1 = __fmaf_rn(db1[2 * e2 + 1], xb1, b1);
+        }
+    }
+    acc0 = pack_f2(a0, b0); acc1 = pack_f2(a1, b1);
+}
+
+// ---- variant 3: dequantisation only (no accumulate): what the FHFMA + LOP3 half costs ----
+__device__ __forceinline__ void q4_trip2_v3(unsigned long long& acc0, unsigned long long& acc1, uint32_t xaddr, uint32_t w0, uint32_t w1,
+                                            const ColMeta& m0, const ColMeta& m1) {
+    const uint4 wa0 = lds_v4(w0), wb0 = lds_v4(w0 ^ 16), wa1 = lds_v4(w1), wb1 = lds_v4(w1 ^ 16);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int qi = 0; qi < 4; qi++) {
+        float da0[8], db0[8], da1[8], db1[8];
+        dequant8(da0, word_of(wa0, qi), m0.s16, m0.nlo, m0.nhi);
+        dequant8(db0, word_of(wb0, qi), m0.s16, m0.nlo, m0.nhi);
+        dequant8(da1, word_of(wa1, qi), m1.s16, m1.nlo, m1.nhi);
+        dequant8(db1, word_of(wb1, qi), m1.s16, m1.nlo, m1.nhi);
+#pragma unroll
+        for (int e = 0; e < 8; e++) { s0 += da0[e]; s1 += db0[e]; s0 += da1[e]; s1 += db1[e]; }   // 1 FADD per weight instead of 1/2 FFMA2
+    }
+    float a, b; unpack_f2(acc0, a, b); acc0 = pack_f2(a + s0, b + s1);
+}
+
+// ---- variant 4: accumulate only (weights taken as raw fp32 bit patterns: no dequantisation) ----
+__device__ __forceinline__ void q4_trip2_v4(unsigned long long& acc0, unsigned long long& acc1, uint32_t xaddr, uint32_t w0, uint32_t w1,
+                                            const ColMeta& m0, const ColMeta& m1) {
+    const uint4 wa0 = lds_v4(w0), wb0 = lds_v4(w0 ^ 16), wa1 = lds_v4(w1), wb1 = lds_v4(w1 ^ 16);
+#pragma unroll
+    for (int qi = 0; qi < 4; qi++) {
+        const float fa0 = __uint_as_float(word_of(wa0, qi)), fb0 = __uint_as_float(word_of(wb0, qi));
+        const float fa1 = __uint_as_float(word_of(wa1, qi)), fb1 = __uint_as_float(word_of(wb1, qi));
+#pragma unroll
+        for (int e2 = 0; e2 < 4; e2++) {
+            unsigned long long xp0, xp1;
+            lds_v2_b64(xaddr + (qi * 4 + e2) * kRowBytes, xp0, xp1);
+            ffma2_pk(acc0, fa0, fb0, xp0);
+            ffma2_pk(acc1, fa1, fb1, xp0);
+            ffma2_pk(acc0, fb0, fa0, xp1);
+            ffma2_pk(acc1, fb1, fa1, xp1);
+        }
+    }
+}
+
+template <int VAR>
+__global__ void __launch_bounds__(384, 1) trip_kernel(const uint32_t* __restrict__ src, float* out, long long* cyc, int T, int ntasks, int active) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int colb = T * 512;
+    const int xs_bytes = T * kTripBytes, w_bytes = 11 * 4 * colb, meta_bytes = 11 * 4 * 64;
+    uint32_t* s32 = reinterpret_cast<uint32_t*>(smem);
+    for (int i = tid; i < (xs_bytes + w_bytes + meta_bytes) / 4; i += blockDim.x) {
+        uint32_t v = src[(i * 7 + blockIdx.x) & 0xFFFFF];
+        if (i < xs_bytes / 4) v = (v & 0x007FFFFFu) | 0x3C000000u;             // x: small positive floats
+        else if (i >= (xs_bytes + w_bytes) / 4) v = (v & 0x03FF03FFu) | 0x20002000u;   // scales: small fp16, zeros: whatever
+        s32[i] = v;
+    }
+    __syncthreads();
+    if (warp >= active) return;
+    const uint32_t base = smem_u32(smem);
+    const uint32_t xs = base, wb = base + xs_bytes + warp * 4 * colb, mb = base + xs_bytes + w_bytes + warp * 4 * 64;
+    const int h = lane >> 4, j = lane & 15, sw = (j >> 2) & 1;
+    const uint32_t w0 = wb + (2 * h) * colb + j * 32 + sw * 16, w1 = w0 + colb;
+    const uint32_t scol0 = mb + (2 * h) * 64, scol1 = scol0 + 64, zcol0 = scol0 + 32, zcol1 = scol1 + 32;
+    float sink = 0.f;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int task = 0; task < ntasks; task++) {
+        unsigned long long acc0 = 0ull, acc1 = 0ull;
+#pragma unroll 1
+        for (int t = 0; t < T; t++) {
+            const ColMeta m0 = col_meta(scol0, zcol0, t & 1, j), m1 = col_meta(scol1, zcol1, t & 1, j);
+            const uint32_t xa = xs + t * kTripBytes + j * 16;
+            if (VAR == 0) q4_trip2(acc0, acc1, xa, w0 + t * 512, w1 + t * 512, m0, m1);
+            if (VAR == 1) q4_trip2_v1(acc0, acc1, xa, w0 + t * 512, w1 + t * 512, m0, m1);
+            if (VAR == 2) q4_trip2_v2(acc0, acc1, xa, w0 + t * 512, w1 + t * 512, m0, m1);
+            if (VAR == 3) q4_trip2_v3(acc0, acc1, xa, w0 + t * 512, w1 + t * 512, m0, m1);
+            if (VAR == 4) q4_trip2_v4(acc0, acc1, xa, w0 + t * 512, w1 + t * 512, m0, m1);
+        }
+        sink += halfwarp_total(acc0) + halfwarp_total(acc1);
+    }
+    const long long t1 = clock64();
+    if (lane == 0) cyc[blockIdx.x * 12 + warp] = t1 - t0;
+    out[blockIdx.x * blockDim.x + tid] = sink;
+}
+
+template <int VAR>
+void run(const char* name, const uint32_t* src, float* out, long long* cyc, int sms) {
+    const int T = 4, ntasks = 64;
+    const size_t smem = (size_t)T * kTripBytes + 11 * 4 * T * 512 + 11 * 4 * 64;
+    cudaFuncSetAttribute(trip_kernel<VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, trip_kernel<VAR>);
+    for (int active : {1, 2, 4, 7, 8, 11}) {
+        cudaMemset(cyc, 0, sizeof(long long) * sms * 12);
+        trip_kernel<VAR><<<sms, 384, smem>>>(src, out, cyc, T, ntasks, active);
+        cudaDeviceSynchronize();
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0);
+        trip_kernel<VAR><<<sms, 384, smem>>>(src, out, cyc, T, ntasks, active);
+        cudaEventRecord(e1);
+        cudaDeviceSynchronize();
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        std::vector<long long> h(sms * 12);
+        cudaMemcpy(h.data(), cyc, sizeof(long long) * sms * 12, cudaMemcpyDeviceToHost);
+        double sum = 0, mx = 0; int n = 0;
+        for (int b = 0; b < sms; b++) for (int w = 0; w < active; w++) { double c = (double)h[b * 12 + w]; sum += c; if (c > mx) mx = c; n++; }
+        const double per_trip = sum / n / (ntasks * T);
+        printf("%-34s regs %3d  active warps %2d: %7.0f clk per warp-trip (slowest warp %7.0f), %5.1f weights/clk/SM  [%0.3f ms, err %d]\n", name, fa.numRegs, active, per_trip,
+               mx / (ntasks * T), active * 4096.0 / (mx / (ntasks * T)), ms, (int)cudaGetLastError());
+    }
+}
+
+int main() {
+    int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    uint32_t* src; float* out; long long* cyc;
+    cudaMalloc(&src, 4 << 20); cudaMalloc(&out, sizeof(float) * sms * 384); cudaMalloc(&cyc, sizeof(long long) * sms * 12);
+    std::vector<uint32_t> h(1 << 20);
+    uint64_t s = 88172645463325252ull;
+    for (auto& v : h) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; v = (uint32_t)s; }
+    cudaMemcpy(src, h.data(), 4 << 20, cudaMemcpyHostToDevice);
+    run<0>("v0 production q4_trip2", src, out, cyc, sms);
+    run<1>("v1 x prefetched per quarter-trip", src, out, cyc, sms);
+    run<2>("v2 FFMA instead of FFMA2", src, out, cyc, sms);
+    run<3>("v3 dequant only (+FADD)", src, out, cyc, sms);
+    run<4>("v4 FFMA2 accumulate only", src, out, cyc, sms);
+    return 0;
+}
