@@ -205,14 +205,18 @@ def test_long_context_fused_equals_op_by_op(eng):
         write_model(E, lib, cfg, 31, path)
         t, s = open_mine(E, lib, path)
         try:
-            steps = 8400
-            prompt = (C.c_int * 3)(1, 35, 72)
+            # a random 8380-token prompt (teacher forcing keeps the context rich: free-running greedy decoding of a tiny random
+            # model collapses to one token), then 20 generated positions
+            steps, n_prompt = 8400, 8380
+            rng = np.random.default_rng(8192)
+            ptoks = [1] + [int(x) for x in rng.integers(3, cfg["vocab_size"], n_prompt - 1)]
+            prompt = (C.c_int * n_prompt)(*ptoks)
             outs, last = [], []
             for fused in (1, 0):
                 lib.lq4_set_option(b"fused", fused)
                 out = (C.c_int * steps)()
                 secs = C.c_double(0)
-                n = lib.lq4_generate_tokens(C.byref(t), C.byref(s), prompt, 3, steps, out, C.byref(secs), 1)
+                n = lib.lq4_generate_tokens(C.byref(t), C.byref(s), prompt, n_prompt, steps, out, C.byref(secs), 1)
                 assert n == steps
                 outs.append(list(out))
                 lg = np.zeros(cfg["vocab_size"], np.uint16)
@@ -220,9 +224,10 @@ def test_long_context_fused_equals_op_by_op(eng):
                 lib.lq4_step(C.byref(t), C.byref(s), 1, lg.ctypes.data_as(C.c_void_p), C.byref(nxt))      # position 8400
                 last.append(lg)
             lib.lq4_set_option(b"fused", 1)
+            assert outs[0][:n_prompt] == ptoks
             bad = [i for i, (a, b) in enumerate(zip(outs[0], outs[1])) if a != b]
             assert not bad, f"fused and op-by-op ids part ways at position {bad[0]}"
             assert (last[0] == last[1]).all(), "logits at position 8400 differ between the fused and the op-by-op path"
-            assert len(set(outs[0][8200:])) > 8, "the long run should not have collapsed to a fixed point"
+            assert np.isfinite(last[0].view(np.float16).astype(np.float32)).all()
         finally:
             lib.lq4_free_transformer(C.byref(t))
