@@ -161,6 +161,17 @@ void lq4_reset(Transformer* t, const int* tokens, int n);   /* generate() init, 
 /* synchronises the engine stream, then copies device memory (e.g. RunState::logits_array, perplexity mode) to the host */
 int lq4_memcpy_to_host(void* dst, const void* src_device, size_t bytes);
 
+/* ---- batched prefill on the tensor cores (new: the reference feeds prompt tokens one by one through decode,
+ * llama2_q4.cu:465-470).  Every projection of batch x seq token rows is one dense INT4 -> fp16 GEMM (tcgen05.mma, accumulators
+ * in tensor memory, X tiles by TMA, W dequantised into shared memory on the fly).  Results agree with the sequential decode
+ * path to fp16 tolerance, not bit for bit (tensor-core summation order). ---- */
+/* y[M][N] = x[M][K] . dequant(w)[N][K]^T (+ y when accum); device pointers, row-major fp16; 1 = unsupported shape (K % 64, N % 128) */
+int lq4_gemm_q4(lq4_half* y, const lq4_half* x, const QWeight* w, int M, int K, int N, int accum);
+/* tokens: host [batch][seq]; logits_last: host [batch][vocab] or NULL; kv_seq >= 0 also fills the KV cache with that sequence and
+ * leaves the positions at seq - 1 so that decode continues; ms_total / ms_gemm: device milliseconds (may be NULL); 1 = unsupported */
+int lq4_prefill(Transformer* t, const int* tokens, int batch, int seq, int kv_seq, lq4_half* logits_last, float* ms_total,
+                float* ms_gemm);
+
 /* ---- tensor parallel, one process per GPU (new: the reference is single-GPU).  Column slices of every matrix per rank;
  * activations are broadcast by peer stores over NVLink (no collective call, no cross-GPU barrier); ids are bit-identical
  * to one GPU.  Order: lq4_tp_config -> lq4_build_transformer -> exchange lq4_tp_export handles -> lq4_tp_import each. ---- */

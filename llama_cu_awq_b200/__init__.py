@@ -99,6 +99,9 @@ _SIGNATURES = {
     "lq4_step": (C.c_int, [C.POINTER(Transformer), C.POINTER(Sampler), C.c_int, _P, C.POINTER(C.c_int)]),
     "lq4_reset": (None, [C.POINTER(Transformer), C.POINTER(C.c_int), C.c_int]),
     "lq4_memcpy_to_host": (C.c_int, [_P, _P, C.c_size_t]),
+    "lq4_gemm_q4": (C.c_int, [_P, _P, C.POINTER(QWeight), C.c_int, C.c_int, C.c_int, C.c_int]),
+    "lq4_prefill": (C.c_int, [C.POINTER(Transformer), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_float),
+                              C.POINTER(C.c_float)]),
     "lq4_tp_config": (C.c_int, [C.c_int, C.c_int]),
     "lq4_tp_export": (C.c_int, [C.POINTER(Transformer), _P]),
     "lq4_tp_import": (C.c_int, [C.POINTER(Transformer), C.c_int, _P]),

@@ -22,6 +22,7 @@
 #include "lq4_types.h"
 #include "kernels_sm100.cuh"
 #include "interp_sm100.cuh"
+#include "prefill_sm100.cuh"
 #include "synth.h"
 #include "../../include/llama_q4_b200.h"
 
@@ -1185,6 +1186,176 @@ int lq4_memcpy_to_host(void* dst, const void* src_device, size_t bytes) {
     cudaError_t e = cudaStreamSynchronize(g.stream);
     if (e == cudaSuccess) e = cudaMemcpy(dst, src_device, bytes, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) { set_err("lq4_memcpy_to_host", e); return 1; }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------- batched prefill (scope row f1)
+// Not in the reference (prompt tokens go one by one through decode, llama2_q4.cu:465-470).  Every projection of a batch of
+// token rows is one dense INT4 -> fp16 GEMM on the tcgen05 tensor cores (prefill_sm100.cuh); parity is fp16 tolerance
+// against the sequential decode path, not bit-exactness.
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !ptr) {
+            fprintf(stderr, "lq4: cuTensorMapEncodeTiled is not available from this driver\n");
+            exit(EXIT_FAILURE);
+        }
+        fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+struct PrefillWs {          // activations of a batch of token rows (device), grown on demand
+    size_t rows = 0;
+    Config cfg = {};
+    half *x = nullptr, *xn = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *att = nullptr, *g = nullptr, *u = nullptr, *xl = nullptr, *logits = nullptr;
+    int* tokens = nullptr;
+    int batch = 0;
+} g_pf;
+
+void pf_free() {
+    cudaFree(g_pf.x); cudaFree(g_pf.xn); cudaFree(g_pf.q); cudaFree(g_pf.k); cudaFree(g_pf.v); cudaFree(g_pf.att); cudaFree(g_pf.g);
+    cudaFree(g_pf.u); cudaFree(g_pf.xl); cudaFree(g_pf.logits); cudaFree(g_pf.tokens);
+    g_pf = PrefillWs();
+}
+
+// Y[M][N] = X[M][K] . dequant(W)[N][K]^T (+ res), fp16 in / fp32 accumulate in tensor memory / fp16 out
+bool gemm_q4_tc(half* y, const half* x, const QWeight* w, int M, int K, int N, const half* res) {
+    if (M < 1 || K % lq4pf::kBK || N % lq4pf::kBN || (((uintptr_t)x | (uintptr_t)y | (uintptr_t)res) & 15)) return false;
+    CUtensorMap tmap;
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(half)};
+    const cuuint32_t box[2] = {(cuuint32_t)lq4pf::kBK, (cuuint32_t)lq4pf::kBM};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { fprintf(stderr, "lq4: cuTensorMapEncodeTiled failed (%d)\n", (int)r); exit(EXIT_FAILURE); }
+    static bool attr = false;
+    if (!attr) {
+        LQ4_CHECK(cudaFuncSetAttribute(lq4pf::gemm_q4_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lq4pf::kSmemBytes));
+        attr = true;
+    }
+    lq4pf::GemmParams p;
+    p.w = w->weight; p.z = w->zeros; p.s = reinterpret_cast<const uint16_t*>(w->scales);
+    p.y = y; p.res = res; p.M = M; p.N = N; p.K = K; p.ldy = N;
+    const int tiles = ((M + lq4pf::kBM - 1) / lq4pf::kBM) * (N / lq4pf::kBN);
+    lq4pf::gemm_q4_tc_kernel<<<std::min(tiles, g.sm_count), lq4pf::kThreads, lq4pf::kSmemBytes, g.stream>>>(tmap, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_err("gemm_q4_tc_kernel launch", e); exit(EXIT_FAILURE); }
+    return true;
+}
+}  // namespace
+
+// Dense INT4 GEMM on the tensor cores: y[M][N] = x[M][K] . W^T (+ y when accum), all device pointers, row-major fp16.
+// Returns 1 when the shape is not supported (K % 64, N % 128, 16-byte alignment); nothing else computes it then.
+int lq4_gemm_q4(half* y, const half* x, const QWeight* w, int M, int K, int N, int accum) {
+    ensure_init();
+    return gemm_q4_tc(y, x, w, M, K, N, accum ? y : nullptr) ? 0 : 1;
+}
+
+// Batched prefill of `batch` sequences of `seq` tokens each (host ids, [batch][seq]).  logits_last (host, [batch][vocab] fp16,
+// may be NULL) receives the logits of every sequence's last position.  kv_seq >= 0: that sequence's rotated K and V rows are
+// also written to the transformer's KV cache and the device / host positions are set to seq - 1 with the tokens copied into
+// SharedData, so that the decode path continues from there (lq4_step / lq4_run_transformer at position seq - 1 recomputes the
+// last prompt position and samples).  ms_total / ms_gemm (may be NULL): device time of the whole pass and of its GEMMs.
+// Returns 0, or 1 when a shape is not supported by the tensor-core GEMM.
+int lq4_prefill(Transformer* t, const int* tokens, int batch, int seq, int kv_seq, half* logits_last, float* ms_total, float* ms_gemm) {
+    ensure_init();
+    Config* p = &t->config;
+    RunState* s = &t->state;
+    TransformerWeights* w = &t->weights;
+    const int dim = p->dim, hidden = p->hidden_dim, hs = dim / p->n_heads;
+    const int kv_dim = (p->dim * p->n_kv_heads) / p->n_heads, kv_mul = p->n_heads / p->n_kv_heads;
+    if (batch < 1 || seq < 1 || seq > p->seq_len || kv_seq >= batch) return 1;
+    if (dim % 128 || kv_dim % 128 || hidden % 128 || dim % 64 || hidden % 64 || hs % 32 || hs > 256 || 256 % lq4pf::kPfQ || hs % (256 / lq4pf::kPfQ)) return 1;
+    const size_t M = (size_t)batch * seq;
+    if (g_pf.rows < M || g_pf.batch < batch || memcmp(&g_pf.cfg, p, sizeof(Config))) {
+        LQ4_CHECK(cudaStreamSynchronize(g.stream));
+        pf_free();
+        g_pf.rows = M; g_pf.cfg = *p; g_pf.batch = batch;
+        LQ4_CHECK(cudaMalloc((void**)&g_pf.x, M * dim * sizeof(half)));
+        LQ4_CHECK(cudaMalloc((void**)&g_pf.xn, M * dim * sizeof(half)));
+        LQ4_CHECK(cudaMalloc((void**)&g_pf.q, M * dim * sizeof(half)));
+        LQ4_CHECK(cudaMalloc((void**)&g_pf.k, M * kv_dim * sizeof(half)));
+        LQ4_CHECK(cudaMalloc((void**)&g_pf.v, M * kv_dim * sizeof(half)));
+        LQ4_CHECK(cudaMalloc((void**)&g_pf.att, M * dim * sizeof(half)));
+        LQ4_CHECK(cudaMalloc((void**)&g_pf.g, M * hidden * sizeof(half)));
+        LQ4_CHECK(cudaMalloc((void**)&g_pf.u, M * hidden * sizeof(half)));
+        LQ4_CHECK(cudaMalloc((void**)&g_pf.xl, (size_t)batch * dim * sizeof(half)));
+        LQ4_CHECK(cudaMalloc((void**)&g_pf.logits, (size_t)batch * p->vocab_size * sizeof(half)));
+        LQ4_CHECK(cudaMalloc((void**)&g_pf.tokens, M * sizeof(int)));
+    }
+    PrefillWs& W = g_pf;
+    const float2* rope_tab = rope_table(p->rope_theta, hs, p->seq_len);
+    LQ4_CHECK(cudaMemcpyAsync(W.tokens, tokens, M * sizeof(int), cudaMemcpyHostToDevice, g.stream));
+    cudaEvent_t ev[4];
+    for (auto& e : ev) LQ4_CHECK(cudaEventCreate(&e));
+    float gemm_ms = 0.0f;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans;
+    auto gemm = [&](half* y, const half* x, const QWeight* qw, int K, int N, const half* res) {
+        cudaEvent_t a = nullptr, b = nullptr;
+        if (ms_gemm) { LQ4_CHECK(cudaEventCreate(&a)); LQ4_CHECK(cudaEventCreate(&b)); LQ4_CHECK(cudaEventRecord(a, g.stream)); }
+        if (!gemm_q4_tc(y, x, qw, (int)M, K, N, res)) { fprintf(stderr, "lq4: prefill GEMM shape K=%d N=%d is not supported\n", K, N); exit(EXIT_FAILURE); }
+        if (ms_gemm) { LQ4_CHECK(cudaEventRecord(b, g.stream)); spans.push_back({a, b}); }
+    };
+    const size_t attn_smem = sizeof(float) * ((size_t)lq4pf::kPfQ * hs + (size_t)lq4pf::kPfQ * seq);
+    if (attn_smem > (size_t)g.max_smem) return 1;
+    allow_smem(lq4pf::attn_prefill_kernel, attn_smem);
+    LQ4_CHECK(cudaEventRecord(ev[0], g.stream));
+    lq4pf::embed_rows_kernel<<<(unsigned)M, 128, 0, g.stream>>>(W.x, w->token_embedding_table, W.tokens, dim);
+    for (int l = 0; l < p->n_layers; l++) {
+        PerLayerWeight& L = w->layers[l];
+        lq4pf::rmsnorm_rows_kernel<<<(unsigned)M, 256, 0, g.stream>>>(W.xn, W.x, L.rms_att_weight, dim);
+        gemm(W.q, W.xn, &L.wq_q, dim, dim, nullptr);
+        gemm(W.k, W.xn, &L.wq_k, dim, kv_dim, nullptr);
+        gemm(W.v, W.xn, &L.wq_v, dim, kv_dim, nullptr);
+        lq4pf::rope_rows_kernel<<<(unsigned)M, 256, 0, g.stream>>>(W.q, W.k, rope_tab, p->n_heads, p->n_kv_heads, hs, seq);
+        if (kv_seq >= 0) {
+            const size_t loff = (size_t)l * p->seq_len * kv_dim, r0 = (size_t)kv_seq * seq * kv_dim;
+            lq4pf::kv_store_kernel<<<seq, 128, 0, g.stream>>>(s->key_cache + loff, s->value_cache + loff, W.k + r0, W.v + r0, kv_dim);
+        }
+        lq4pf::attn_prefill_kernel<<<dim3((seq + lq4pf::kPfQ - 1) / lq4pf::kPfQ, p->n_heads, batch), 256, attn_smem, g.stream>>>(
+            W.att, W.q, W.k, W.v, seq, p->n_heads, kv_mul, hs, (float)(1.0 / sqrt((double)hs)));
+        gemm(W.x, W.att, &L.wq_o, dim, dim, W.x);
+        lq4pf::rmsnorm_rows_kernel<<<(unsigned)M, 256, 0, g.stream>>>(W.xn, W.x, L.rms_ffn_weight, dim);
+        gemm(W.g, W.xn, &L.wq_gate, dim, hidden, nullptr);
+        gemm(W.u, W.xn, &L.wq_up, dim, hidden, nullptr);
+        const size_t nh = M * hidden;
+        lq4pf::silu_mul_kernel<<<(unsigned)((nh + 255) / 256), 256, 0, g.stream>>>(W.g, W.g, W.u, nh);
+        gemm(W.x, W.g, &L.wq_down, hidden, dim, W.x);
+    }
+    // last position of every sequence: final RMSNorm + classifier (the decode path's fp16 GEMV, one row per sequence)
+    for (int b = 0; b < batch; b++) {
+        lq4pf::rmsnorm_rows_kernel<<<1, 256, 0, g.stream>>>(W.xl + (size_t)b * dim, W.x + ((size_t)b * seq + seq - 1) * dim, w->rms_final_weight, dim);
+        lq4_matmul_fp16(W.logits + (size_t)b * p->vocab_size, W.xl + (size_t)b * dim, w->wcls, dim, p->vocab_size, 1, 0, 0, 0, -1, 1.0f);
+    }
+    LQ4_CHECK(cudaEventRecord(ev[1], g.stream));
+    if (kv_seq >= 0) {        // hand over to the decode path at the last prompt position
+        const int pos = seq - 1;
+        LQ4_CHECK(cudaMemcpyAsync(s->pos, &pos, sizeof(int), cudaMemcpyHostToDevice, g.stream));
+    }
+    LQ4_CHECK(cudaStreamSynchronize(g.stream));
+    if (kv_seq >= 0) {
+        s->shared_data->pos = seq - 1;
+        memcpy((void*)s->shared_data->tokens, tokens + (size_t)kv_seq * seq, sizeof(int) * seq);
+    }
+    if (ms_total) LQ4_CHECK(cudaEventElapsedTime(ms_total, ev[0], ev[1]));
+    for (auto& sp : spans) {
+        float ms = 0.0f;
+        LQ4_CHECK(cudaEventElapsedTime(&ms, sp.first, sp.second));
+        gemm_ms += ms;
+        cudaEventDestroy(sp.first); cudaEventDestroy(sp.second);
+    }
+    if (ms_gemm) *ms_gemm = gemm_ms;
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (logits_last) LQ4_CHECK(cudaMemcpy(logits_last, W.logits, (size_t)batch * p->vocab_size * sizeof(half), cudaMemcpyDeviceToHost));
     return 0;
 }
 
