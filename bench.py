@@ -382,7 +382,8 @@ def prefill_record(eng, lib, E, cfg, batch=8, seq=2048):
             "roofline": {"bound": "tensor", "kernel": "gemm_q4_tc_kernel (tcgen05.mma kind::f16, INT4 weights dequantised into shared memory, TMEM accumulators)",
                          "achieved": tf, "peak": tflops_peak, "unit": "TFLOP/s", "frac": tf / tflops_peak, "peak_source": src,
                          "how": "2*M*K*N over the 7 projections x 32 layers / summed CUDA-event time of the GEMM launches"},
-            "note": "the causal attention of the prefill is still a CUDA-core kernel and dominates ms_total at seq 2048; the GEMMs are the tensor-core path"}
+            "note": "ms_total also holds the causal attention (mma.sync m16n8k16 flash kernel), RMSNorm, RoPE, SiLU and the classifier of the 8 last positions; "
+                    "the projections are the tcgen05 path the roofline object describes"}
 
 
 def roofline_record(E, cfg, model, K, ms, peak, peak_src, share=1):

@@ -1306,8 +1306,10 @@ int lq4_prefill(Transformer* t, const int* tokens, int batch, int seq, int kv_se
         if (ms_gemm) { LQ4_CHECK(cudaEventRecord(b, g.stream)); spans.push_back({a, b}); }
     };
     const size_t attn_smem = sizeof(float) * ((size_t)lq4pf::kPfQ * hs + (size_t)lq4pf::kPfQ * seq);
-    if (attn_smem > (size_t)g.max_smem) return 1;
-    allow_smem(lq4pf::attn_prefill_kernel, attn_smem);
+    if (hs != 128 && hs != 64) {
+        if (attn_smem > (size_t)g.max_smem) return 1;
+        allow_smem(lq4pf::attn_prefill_kernel, attn_smem);
+    }
     LQ4_CHECK(cudaEventRecord(ev[0], g.stream));
     lq4pf::embed_rows_kernel<<<(unsigned)M, 128, 0, g.stream>>>(W.x, w->token_embedding_table, W.tokens, dim);
     for (int l = 0; l < p->n_layers; l++) {
@@ -1321,8 +1323,15 @@ int lq4_prefill(Transformer* t, const int* tokens, int batch, int seq, int kv_se
             const size_t loff = (size_t)l * p->seq_len * kv_dim, r0 = (size_t)kv_seq * seq * kv_dim;
             lq4pf::kv_store_kernel<<<seq, 128, 0, g.stream>>>(s->key_cache + loff, s->value_cache + loff, W.k + r0, W.v + r0, kv_dim);
         }
-        lq4pf::attn_prefill_kernel<<<dim3((seq + lq4pf::kPfQ - 1) / lq4pf::kPfQ, p->n_heads, batch), 256, attn_smem, g.stream>>>(
-            W.att, W.q, W.k, W.v, seq, p->n_heads, kv_mul, hs, (float)(1.0 / sqrt((double)hs)));
+        const float att_alpha = (float)(1.0 / sqrt((double)hs));
+        const dim3 fa_grid((seq + lq4pf::kFaQ - 1) / lq4pf::kFaQ, p->n_heads, batch);
+        if (hs == 128)
+            lq4pf::attn_prefill_mma_kernel<128><<<fa_grid, 128, 0, g.stream>>>(W.att, W.q, W.k, W.v, seq, p->n_heads, kv_mul, att_alpha);
+        else if (hs == 64)
+            lq4pf::attn_prefill_mma_kernel<64><<<fa_grid, 128, 0, g.stream>>>(W.att, W.q, W.k, W.v, seq, p->n_heads, kv_mul, att_alpha);
+        else        // other head sizes: the CUDA-core kernel
+            lq4pf::attn_prefill_kernel<<<dim3((seq + lq4pf::kPfQ - 1) / lq4pf::kPfQ, p->n_heads, batch), 256, attn_smem, g.stream>>>(
+                W.att, W.q, W.k, W.v, seq, p->n_heads, kv_mul, hs, att_alpha);
         gemm(W.x, W.att, &L.wq_o, dim, dim, W.x);
         lq4pf::rmsnorm_rows_kernel<<<(unsigned)M, 256, 0, g.stream>>>(W.xn, W.x, L.rms_ffn_weight, dim);
         gemm(W.g, W.xn, &L.wq_gate, dim, hidden, nullptr);

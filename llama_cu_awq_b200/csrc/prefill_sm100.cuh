@@ -393,6 +393,123 @@ __global__ void __launch_bounds__(256) attn_prefill_kernel(half* out, const half
     }
 }
 
+// Causal attention on the legacy tensor-core path (mma.sync m16n8k16, fp16 in / fp32 accumulate): one CTA of 4 warps per
+// (sequence, head, 64 query rows), 16 rows per warp; K and V tiles of 64 keys staged in shared memory by cp.async, online
+// softmax in fp32 (scores rounded to fp16 where the decode path rounds them), P.V with V fragments by ldmatrix.trans.
+// The projections are the tcgen05 path of this round; a tcgen05 attention (S and O in tensor memory) is the next step.
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+constexpr int kFaQ = 64, kFaK = 64;
+template <int HS>
+__global__ void __launch_bounds__(128) attn_prefill_mma_kernel(half* out, const half* __restrict__ q, const half* __restrict__ k, const half* __restrict__ v,
+                                                               int seq, int n_heads, int kv_mul, float alpha) {
+    constexpr int LD = HS + 8;                                     // padded row (halfs): conflict-free fragment loads
+    __shared__ __align__(16) half Ks[kFaK * LD];
+    __shared__ __align__(16) half Vs[kFaK * LD];
+    const int q0 = blockIdx.x * kFaQ, h = blockIdx.y, b = blockIdx.z;
+    const int kvh = h / kv_mul, kv_dim = (n_heads / kv_mul) * HS, dim = n_heads * HS;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const size_t row0 = (size_t)b * seq;
+    const int r_lo = q0 + warp * 16 + g, r_hi = r_lo + 8;          // this thread's two query rows
+    // Q fragments (A operand), straight from global memory
+    uint32_t qa[HS / 16][4];
+    {
+        const half* qlo = q + (row0 + min(r_lo, seq - 1)) * dim + h * HS;
+        const half* qhi = q + (row0 + min(r_hi, seq - 1)) * dim + h * HS;
+#pragma unroll
+        for (int ks = 0; ks < HS / 16; ks++) {
+            qa[ks][0] = *reinterpret_cast<const uint32_t*>(qlo + ks * 16 + 2 * t);
+            qa[ks][1] = *reinterpret_cast<const uint32_t*>(qhi + ks * 16 + 2 * t);
+            qa[ks][2] = *reinterpret_cast<const uint32_t*>(qlo + ks * 16 + 8 + 2 * t);
+            qa[ks][3] = *reinterpret_cast<const uint32_t*>(qhi + ks * 16 + 8 + 2 * t);
+        }
+    }
+    float o[HS / 8][4];
+#pragma unroll
+    for (int d = 0; d < HS / 8; d++) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.0f;
+    float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.0f, l_hi = 0.0f;
+    const int last_key = min(q0 + kFaQ, seq) - 1;
+    for (int k0 = 0; k0 <= last_key; k0 += kFaK) {
+        __syncthreads();                                           // the previous tile is no longer read
+        for (int idx = tid; idx < kFaK * (HS / 8); idx += 128) {
+            const int r = idx / (HS / 8), c = idx % (HS / 8);
+            const int key = min(k0 + r, seq - 1);
+            lq4::cp_async16(smem_u32(Ks + r * LD + c * 8), k + (row0 + key) * kv_dim + kvh * HS + c * 8);
+            lq4::cp_async16(smem_u32(Vs + r * LD + c * 8), v + (row0 + key) * kv_dim + kvh * HS + c * 8);
+        }
+        lq4::cp_async_commit();
+        lq4::cp_async_wait<0>();
+        __syncthreads();
+        // ---- S = Q K^T (16 rows x 64 keys per warp) ----
+        float sacc[kFaK / 8][4];
+#pragma unroll
+        for (int n = 0; n < kFaK / 8; n++) sacc[n][0] = sacc[n][1] = sacc[n][2] = sacc[n][3] = 0.0f;
+#pragma unroll
+        for (int ks = 0; ks < HS / 16; ks++) {
+#pragma unroll
+            for (int n = 0; n < kFaK / 8; n++) {
+                const half* kr = Ks + (n * 8 + g) * LD + ks * 16 + 2 * t;
+                mma16816(sacc[n], qa[ks], *reinterpret_cast<const uint32_t*>(kr), *reinterpret_cast<const uint32_t*>(kr + 8));
+            }
+        }
+        // ---- scale, round like the decode path, causal mask, online softmax ----
+        float mx_lo = m_lo, mx_hi = m_hi;
+#pragma unroll
+        for (int n = 0; n < kFaK / 8; n++) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int key = k0 + n * 8 + 2 * t + (e & 1), row = (e < 2) ? r_lo : r_hi;
+                float sv = __half2float(__float2half_rn(sacc[n][e] * alpha));
+                if (key > row || key >= seq) sv = -INFINITY;
+                sacc[n][e] = sv;
+                if (e < 2) mx_lo = fmaxf(mx_lo, sv); else mx_hi = fmaxf(mx_hi, sv);
+            }
+        }
+        mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1)); mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+        mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1)); mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+        // every row of the block sees key 0 in the first tile, so the running maxima are finite from the first tile on
+        const float c_lo = expf(m_lo - mx_lo), c_hi = expf(m_hi - mx_hi);
+        m_lo = mx_lo; m_hi = mx_hi;
+        float s_lo = 0.0f, s_hi = 0.0f;
+        uint32_t pa[kFaK / 16][4];
+#pragma unroll
+        for (int n = 0; n < kFaK / 8; n++) {
+            const float p0 = expf(sacc[n][0] - m_lo), p1 = expf(sacc[n][1] - m_lo), p2 = expf(sacc[n][2] - m_hi), p3 = expf(sacc[n][3] - m_hi);
+            s_lo += p0 + p1; s_hi += p2 + p3;
+            pa[n >> 1][(n & 1) * 2] = pack_h2(p0, p1);
+            pa[n >> 1][(n & 1) * 2 + 1] = pack_h2(p2, p3);
+        }
+        s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 1); s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 2);
+        s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 1); s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 2);
+        l_lo = l_lo * c_lo + s_lo; l_hi = l_hi * c_hi + s_hi;
+#pragma unroll
+        for (int d = 0; d < HS / 8; d++) { o[d][0] *= c_lo; o[d][1] *= c_lo; o[d][2] *= c_hi; o[d][3] *= c_hi; }
+        // ---- O += P V ----
+#pragma unroll
+        for (int kk = 0; kk < kFaK / 16; kk++) {
+#pragma unroll
+            for (int d = 0; d < HS / 8; d++) {
+                uint32_t b0, b1;
+                const uint32_t addr = smem_u32(Vs + (kk * 16 + (lane & 15)) * LD + d * 8);
+                asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(addr));
+                mma16816(o[d], pa[kk], b0, b1);
+            }
+        }
+    }
+    const float i_lo = 1.0f / l_lo, i_hi = 1.0f / l_hi;
+#pragma unroll
+    for (int d = 0; d < HS / 8; d++) {
+        if (r_lo < seq) *reinterpret_cast<uint32_t*>(out + (row0 + r_lo) * dim + h * HS + d * 8 + 2 * t) = pack_h2(o[d][0] * i_lo, o[d][1] * i_lo);
+        if (r_hi < seq) *reinterpret_cast<uint32_t*>(out + (row0 + r_hi) * dim + h * HS + d * 8 + 2 * t) = pack_h2(o[d][2] * i_hi, o[d][3] * i_hi);
+    }
+}
+
 // rows of one sequence -> its KV-cache layer (so that decode can continue after the prefill)
 __global__ void kv_store_kernel(half* kc, half* vc, const half* __restrict__ k, const half* __restrict__ v, int kv_dim) {
     const int pos = blockIdx.x;
