@@ -67,6 +67,7 @@ struct Engine {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int opt_pdl = 1;        // generic per-op kernels only
+    int opt_opk = 0;        // operator API: 1 = stand-alone kernels chained by programmatic dependent launch instead of one-op launches of the persistent kernel
     int opt_fused = 1;      // run_llama_network: one persistent launch per token (1) or op-by-op like the reference (0)
     int opt_nwc = 0;        // consumer warps per CTA; 0 = choose per model
     int opt_nslots = 0;     // cap on ring slots; 0 = as many as fit
@@ -118,6 +119,7 @@ void ensure_init() {
     if (!g.stream) { LQ4_CHECK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking)); g.own_stream = true; }
     const char* env;
     if ((env = getenv("LQ4_PDL"))) g.opt_pdl = atoi(env);
+    if ((env = getenv("LQ4_OPK"))) g.opt_opk = atoi(env);
     if ((env = getenv("LQ4_FUSED"))) g.opt_fused = atoi(env);
     if ((env = getenv("LQ4_NWC"))) { g.opt_nwc = atoi(env); if (g.opt_nwc != 0 && g.opt_nwc < 8) g.opt_nwc = 8; }
     if ((env = getenv("LQ4_NOMATH"))) g.opt_nomath = atoi(env);
@@ -483,6 +485,7 @@ static void drop_net_plans() {
 void lq4_set_option(const char* name, int value) {
     ensure_init();
     if (!strcmp(name, "pdl")) g.opt_pdl = value;
+    else if (!strcmp(name, "opk")) g.opt_opk = value;
     else if (!strcmp(name, "fused")) g.opt_fused = value;
     else if (!strcmp(name, "nwc")) {
         if (value != 0 && value < 8) { fprintf(stderr, "lq4: nwc must be 0 (default) or >= 8 (RMSNorm staging and the attention op need 8 consumer warps); ignored\n"); return; }
@@ -515,7 +518,7 @@ int lq4_debug_trace(unsigned long long* out, int* kinds, int max) {
 // ---------------------------------------------------------------------------------- operator API
 void lq4_rmsnorm(half* o, half* x, half* weight, int size) {
     ensure_init();
-    rmsnorm_kernel<<<1, 1024, 0, g.stream>>>(o, x, weight, size);
+    launch(rmsnorm_kernel, dim3(1), dim3(1024), 0, g.opt_opk && g.opt_pdl, o, (const half*)x, (const half*)weight, size);
 }
 
 void lq4_matmul_fp16(half* xout, half* x, half* w, int n, int d, int batch, int x_stride, int w_stride, int op_stride,
@@ -545,7 +548,7 @@ void lq4_matmul_q4(half* xout, half* x, const QWeight* w, int inpSize, int opSiz
     op.x = x; op.accum = accum;
     const bool cache_row = (loff != -1);
     set_seg(op.seg[0], w, xout, opSize, cache_row ? loff : 0, cache_row ? opSize : 0);
-    if (q4_op_shape(op, inpSize, &opSize, 1, false)) {
+    if (!g.opt_opk && q4_op_shape(op, inpSize, &opSize, 1, false)) {
         run_single(op, cache_row ? pPos : nullptr);
         return;
     }
@@ -553,7 +556,7 @@ void lq4_matmul_q4(half* xout, half* x, const QWeight* w, int inpSize, int opSiz
     p.x = x; p.K = inpSize;
     p.m[0] = qw_view(w); p.n[0] = opSize; p.out[0] = xout;
     p.accum = accum; p.loff = loff; p.pPos = cache_row ? pPos : nullptr;
-    launch_gemv<GEMV_PLAIN>(p, opSize / 4, false);
+    launch_gemv<GEMV_PLAIN>(p, opSize / 4, g.opt_opk && g.opt_pdl);
 }
 
 void lq4_qkv_matvec(half* q, half* key_cache, half* value_cache, half* x, const QWeight* qw, const QWeight* kw,
@@ -568,7 +571,7 @@ void lq4_qkv_matvec(half* q, half* key_cache, half* value_cache, half* x, const 
     set_seg(op.seg[1], kw, key_cache, opSize, loff, opSize);
     set_seg(op.seg[2], vw, value_cache, opSize, loff, opSize);
     const int nc[3] = {opSize, opSize, opSize};
-    if (q4_op_shape(op, inpSize, nc, 3, false)) {
+    if (!g.opt_opk && q4_op_shape(op, inpSize, nc, 3, false)) {
         run_single(op, pPos);
         return;
     }
@@ -578,7 +581,7 @@ void lq4_qkv_matvec(half* q, half* key_cache, half* value_cache, half* x, const 
     p.n[0] = p.n[1] = p.n[2] = opSize;
     p.out[0] = q; p.out[1] = key_cache; p.out[2] = value_cache;
     p.loff = loff; p.pPos = pPos;
-    launch_gemv<GEMV_QKV>(p, 3 * opSize / 4, false);
+    launch_gemv<GEMV_QKV>(p, 3 * opSize / 4, g.opt_opk && g.opt_pdl);
 }
 
 void lq4_ffn_matvec_silu(half* xout, half* x, const QWeight* gate_w, const QWeight* up_w, int inpSize, int opSize) {
@@ -591,7 +594,7 @@ void lq4_ffn_matvec_silu(half* xout, half* x, const QWeight* gate_w, const QWeig
     set_seg(op.seg[0], gate_w, xout, opSize, 0, 0);
     set_seg(op.seg[1], up_w, xout, opSize, 0, 0);
     const int nc[2] = {opSize, opSize};
-    if (q4_op_shape(op, inpSize, nc, 2, true)) {
+    if (!g.opt_opk && q4_op_shape(op, inpSize, nc, 2, true)) {
         run_single(op, nullptr);
         return;
     }
@@ -600,13 +603,13 @@ void lq4_ffn_matvec_silu(half* xout, half* x, const QWeight* gate_w, const QWeig
     p.m[0] = qw_view(gate_w); p.m[1] = qw_view(up_w);
     p.n[0] = opSize; p.out[0] = xout;
     p.loff = -1;
-    launch_gemv<GEMV_FFN>(p, opSize / 2, false);
+    launch_gemv<GEMV_FFN>(p, opSize / 2, g.opt_opk && g.opt_pdl);
 }
 
 void lq4_rope_rotation(half* q, half* k, int num_heads, int num_kv_heads, int head_size, int* pPos, int loff,
                        float rope_theta) {
     ensure_init();
-    rope_kernel<<<num_heads, head_size / 2, 0, g.stream>>>(q, k, num_kv_heads, head_size, pPos, loff, rope_theta);
+    launch(rope_kernel, dim3(num_heads), dim3(head_size / 2), 0, g.opt_opk && g.opt_pdl, q, k, num_kv_heads, head_size, (const int*)pPos, loff, rope_theta);
 }
 
 static void fill_attn_op(Op& op, half* output, half* q, half* key_cache, half* value_cache, half* att, int num_heads,
@@ -627,7 +630,7 @@ static void fill_attn_op(Op& op, half* output, half* q, half* key_cache, half* v
 void lq4_multi_head_attention(half* output, half* q, half* key_cache, half* value_cache, half* att, int num_heads,
                               int head_size, int kv_mul, int max_seq_len, int* pPos) {
     ensure_init();
-    if (head_size != 32 && head_size != 64 && head_size != 128 && head_size % 32 == 0 && head_size <= 256) {
+    if ((g.opt_opk || (head_size != 32 && head_size != 64 && head_size != 128)) && head_size % 32 == 0 && head_size <= 256) {
         // other head sizes: the stand-alone kernel (same arithmetic, one block of 1024 threads per head)
         AttnParams ap = {};
         ap.out = output; ap.q = q; ap.kcache = key_cache; ap.vcache = value_cache; ap.att_out = att;
@@ -636,7 +639,7 @@ void lq4_multi_head_attention(half* output, half* q, half* key_cache, half* valu
         ap.exp16 = max_seq_len > MAX_SEQ_LEN_SMEM_KERNEL;
         const size_t smem = sizeof(float) * (size_t)(head_size + 32 + 4 + ((max_seq_len + 3) & ~3) + 32 * head_size);
         allow_smem(attention_kernel, smem);
-        launch(attention_kernel, dim3(num_heads), dim3(kAttnThreads), smem, false, ap);
+        launch(attention_kernel, dim3(num_heads), dim3(kAttnThreads), smem, g.opt_opk && g.opt_pdl, ap);
         return;
     }
     Op op;
@@ -653,8 +656,8 @@ static void run_network_unfused(int* pPos, Config* p, RunState* s, TransformerWe
     const int head_size = dim / p->n_heads;
     const int kv_dim = (p->dim * p->n_kv_heads) / p->n_heads;
     const int kv_mul = p->n_heads / p->n_kv_heads;
-    copy_embedding_kernel<<<divUp(dim, 256), 256, 0, g.stream>>>(x, w->token_embedding_table, dim,
-                                                                 s->shared_data->tokens, pPos);
+    launch(copy_embedding_kernel, dim3(divUp(dim, 256)), dim3(256), 0, g.opt_opk && g.opt_pdl, x, (const half*)w->token_embedding_table, dim,
+           (const int*)s->shared_data->tokens, (const int*)pPos);
     for (int l = 0; l < p->n_layers; l++) {
         PerLayerWeight& L = w->layers[l];
         lq4_rmsnorm(s->xb, x, L.rms_att_weight, dim);
@@ -1228,7 +1231,7 @@ void pf_free() {
 
 // Y[M][N] = X[M][K] . dequant(W)[N][K]^T (+ res), fp16 in / fp32 accumulate in tensor memory / fp16 out
 bool gemm_q4_tc(half* y, const half* x, const QWeight* w, int M, int K, int N, const half* res) {
-    if (M < 1 || K % lq4pf::kBK || N % lq4pf::kBN || (((uintptr_t)x | (uintptr_t)y | (uintptr_t)res) & 15)) return false;
+    if (M < 1 || K % lq4pf::kBK || N % lq4pf::kBNmin || (((uintptr_t)x | (uintptr_t)y | (uintptr_t)res) & 15)) return false;
     CUtensorMap tmap;
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
     const cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(half)};
@@ -1239,14 +1242,23 @@ bool gemm_q4_tc(half* y, const half* x, const QWeight* w, int M, int K, int N, c
     if (r != CUDA_SUCCESS) { fprintf(stderr, "lq4: cuTensorMapEncodeTiled failed (%d)\n", (int)r); exit(EXIT_FAILURE); }
     static bool attr = false;
     if (!attr) {
-        LQ4_CHECK(cudaFuncSetAttribute(lq4pf::gemm_q4_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lq4pf::kSmemBytes));
+        LQ4_CHECK(cudaFuncSetAttribute(lq4pf::gemm_q4_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lq4pf::Geo<128>::kSmemBytes));
+        LQ4_CHECK(cudaFuncSetAttribute(lq4pf::gemm_q4_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lq4pf::Geo<256>::kSmemBytes));
         attr = true;
     }
     lq4pf::GemmParams p;
     p.w = w->weight; p.z = w->zeros; p.s = reinterpret_cast<const uint16_t*>(w->scales);
     p.y = y; p.res = res; p.M = M; p.N = N; p.K = K; p.ldy = N;
-    const int tiles = ((M + lq4pf::kBM - 1) / lq4pf::kBM) * (N / lq4pf::kBN);
-    lq4pf::gemm_q4_tc_kernel<<<std::min(tiles, g.sm_count), lq4pf::kThreads, lq4pf::kSmemBytes, g.stream>>>(tmap, p);
+    const int num_m = (M + lq4pf::kBM - 1) / lq4pf::kBM;
+    // 256-wide tiles halve the L2 traffic of X; the narrow tile serves N % 256 != 0 and problems too small to fill the SMs otherwise
+    const bool wide = (N % 256 == 0) && (num_m * (N / 256) >= g.sm_count || getenv("LQ4_GEMM_WIDE"));
+    if (wide) {
+        const int tiles = num_m * (N / 256);
+        lq4pf::gemm_q4_tc_kernel<256><<<std::min(tiles, g.sm_count), lq4pf::kThreads, lq4pf::Geo<256>::kSmemBytes, g.stream>>>(tmap, p);
+    } else {
+        const int tiles = num_m * (N / 128);
+        lq4pf::gemm_q4_tc_kernel<128><<<std::min(tiles, g.sm_count), lq4pf::kThreads, lq4pf::Geo<128>::kSmemBytes, g.stream>>>(tmap, p);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_err("gemm_q4_tc_kernel launch", e); exit(EXIT_FAILURE); }
     return true;

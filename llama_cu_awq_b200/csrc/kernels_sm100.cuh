@@ -575,6 +575,8 @@ __global__ void rope_table_kernel(float2* tab, int seq_len, int head_size, float
 //   q: out0 = fma(q0,c,-(q1*s))  out1 = fma(q1,c,q0*s)      k: out0 = fma(k0,c,-(k1*s))  out1 = fma(k0,s,k1*c)
 __global__ void rope_kernel(half* sq, half* sk_base, int num_kv_heads, int head_size, const int* pPos, int loff,
                             float rope_theta) {
+    griddep_launch();
+    griddep_wait();
     const int pos = *pPos;
     const int h = blockIdx.x, i = threadIdx.x;
     const float2 cs = rope_cos_sin(pos, i, head_size, rope_theta);
@@ -595,6 +597,8 @@ __global__ void rope_kernel(half* sq, half* sk_base, int num_kv_heads, int head_
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) rmsnorm_kernel(half* o, const half* x, const half* weight, int size) {
     __shared__ float red[32];
+    griddep_launch();
+    griddep_wait();
     const float scale = block_rms_scale<1024>(x, size, red);
     for (int k = threadIdx.x; k < size; k += 1024) {
         float val = __half2float(x[k]);
@@ -606,6 +610,8 @@ __global__ void __launch_bounds__(1024) rmsnorm_kernel(half* o, const half* x, c
 __global__ void copy_embedding_kernel(half* x, const half* __restrict__ table, int size, const int* tokens,
                                       const int* pPos) {
     const int index = blockIdx.x * blockDim.x + threadIdx.x;
+    griddep_launch();
+    griddep_wait();
     if (index >= size) return;
     const int token = tokens[*pPos];
     x[index] = table[(size_t)token * size + index];

@@ -33,20 +33,25 @@ using lq4::mbar_arrive;
 using lq4::mbar_arrive_expect_tx;
 using lq4::mbar_wait;
 
-constexpr int kBM = 256, kBN = 128, kBK = 64;      // CTA tile; the MMA atom is 128 x 128 x 16
-constexpr int kStages = 4;
+constexpr int kBM = 256, kBK = 64;                 // CTA tile rows / k-block; the MMA atom is 128 x BN x 16, BN = 128 or 256
+constexpr int kBNmin = 128;
 constexpr int kABytes = kBM * kBK * 2;             // 32 KB
-constexpr int kBBytes = kBN * kBK * 2;             // 16 KB
-constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kDequantWarps = 8, kEpiWarps = 4;
 constexpr int kThreads = 32 * (2 + kDequantWarps + kEpiWarps);      // 448
 constexpr int kFirstDequantWarp = 2, kFirstEpiWarp = 2 + kDequantWarps;
 constexpr int kTmemCols = 512;
-constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + 1024;    // alignment slack + ring + barriers
-
-// instruction descriptor of tcgen05.mma.kind::f16 (cute/arch/mma_sm100_desc.hpp, InstrDescriptor): D = F32 (bits 4-5 = 1),
-// A = B = F16 (0), both K-major (0), N >> 3 at bit 17, M >> 4 at bit 24
-constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// BN = 256 halves the L2 -> SM traffic of the X tiles (measured: at BN = 128 the kernel moved 7.7 TB/s out of L2 and the tensor
+// pipe was busy 52 % of the time); its two 128 x 256 accumulators fill the tensor memory, so the epilogue is not double-buffered
+template <int BN> struct Geo {
+    static constexpr int kBBytes = BN * kBK * 2;                     // 16 / 32 KB
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (BN == 128) ? 4 : 3;              // 192 KB either way
+    static constexpr int kAccBufs = (BN == 128) ? 2 : 1;
+    static constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + 1024;    // alignment slack + ring + barriers
+    // instruction descriptor of tcgen05.mma.kind::f16 (cute/arch/mma_sm100_desc.hpp, InstrDescriptor): D = F32 (bits 4-5 = 1),
+    // A = B = F16 (0), both K-major (0), N >> 3 at bit 17, M >> 4 at bit 24
+    static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+};
 
 // shared-memory matrix descriptor, K-major, SWIZZLE_128B (SmemDescriptor): start address >> 4, leading byte offset 1 (ignored
 // for swizzled K-major), stride byte offset = 8 rows x 128 B = 1024 >> 4, version 1 (Blackwell) at bit 46, layout type 2 at bit 61
@@ -99,7 +104,10 @@ __device__ __forceinline__ void tile_coord(int tile, int num_m, int num_n, int& 
     n_blk = r / gm;
 }
 
+template <int BN>
 __global__ void __launch_bounds__(kThreads, 1) gemm_q4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams p) {
+    constexpr int kBN = BN, kStages = Geo<BN>::kStages, kStageBytes = Geo<BN>::kStageBytes, kAccBufs = Geo<BN>::kAccBufs;
+    constexpr uint32_t kIdesc = Geo<BN>::kIdesc;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B tiles need 1024-byte alignment
     const uint32_t bars = base + kStages * kStageBytes;
@@ -118,7 +126,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_q4_tc_kernel(const __grid_co
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) { mbar_init(full_a(s), 1); mbar_init(full_b(s), kDequantWarps); mbar_init(empty(s), 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), kEpiWarps); }
+        for (int b = 0; b < kAccBufs; b++) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {      // tensor memory: the whole 512 columns (one CTA per SM)
@@ -150,10 +158,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_q4_tc_kernel(const __grid_co
         // ===== MMA issuer =====
         uint32_t it = 0, tcount = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
-            const int buf = tcount & 1;
-            mbar_wait(tmem_empty(buf), ((tcount >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator pair
+            const int buf = tcount % kAccBufs;
+            mbar_wait(tmem_empty(buf), ((tcount / kAccBufs) & 1) ^ 1);       // the epilogue has drained this accumulator pair
             tc_fence_after();
-            const uint32_t d0 = tmem_base + buf * 256, d1 = d0 + 128;
+            const uint32_t d0 = tmem_base + buf * 256, d1 = d0 + kBN;
             for (int kb = 0; kb < num_k; kb++, it++) {
                 const int s = it % kStages;
                 const uint32_t ph = (it / kStages) & 1;
@@ -176,8 +184,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_q4_tc_kernel(const __grid_co
         }
     } else if (warp < kFirstEpiWarp) {
         // ===== INT4 -> fp16 dequantisation into the B stage =====
+        // BN = 128: thread = (row, 16-byte half of the row's 32 packed bytes); BN = 256: thread = row, both halves
+        constexpr int kHalves = BN / 128;                           // 16-byte pieces per thread and k-block
         const int dt = threadIdx.x - 32 * kFirstDequantWarp;       // 0..255
-        const int row = dt >> 1, hw = dt & 1;                      // row of the B tile, which 16-byte half of its 32 packed bytes
+        const int row = (BN == 128) ? dt >> 1 : dt, hw0 = (BN == 128) ? (dt & 1) : 0;
         const int G = (p.K + 127) >> 7, zh = (G + 7) >> 3;
         const uint32_t dst_row = (uint32_t)(row >> 3) * 1024 + (uint32_t)(row & 7) * 128;
         uint32_t it = 0;
@@ -185,50 +195,64 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_q4_tc_kernel(const __grid_co
             int m_blk, n_blk;
             tile_coord(tile, num_m, num_n, m_blk, n_blk);
             const int n = n_blk * kBN + row;
-            const uint32_t* wrow = p.w + (size_t)n * (p.K >> 3) + hw * 4;
+            const uint32_t* wrow = p.w + (size_t)n * (p.K >> 3) + hw0 * 4;
             const uint16_t* srow = p.s + (size_t)n * G;
             const uint32_t* zrow = p.z + (size_t)n * zh;
-            uint4 wq = lq4::ldg_stream_v4(wrow);
-            uint32_t sc = lq4::ldg_stream_u16(srow), zw = lq4::ldg_stream_u32(zrow);
+            // Packed words, scale and zero word of k-blocks kb and kb + 1 sit in registers; those of kb + 2 are requested before kb is
+            // converted (two stage-times of load latency hidden: with one, ncu showed the dequant warps waiting on these loads)
+            uint4 wa[kHalves], wb[kHalves];
+            uint32_t sa, sb, za, zb;
+            auto load_kb = [&](int kb, uint4 (&wd)[kHalves], uint32_t& sd, uint32_t& zd) {
+                if (kb < num_k) {
+#pragma unroll
+                    for (int hh = 0; hh < kHalves; hh++) wd[hh] = lq4::ldg_stream_v4(wrow + (size_t)kb * 8 + hh * 4);
+                    const int gg = kb >> 1;
+                    sd = lq4::ldg_stream_u16(srow + gg);
+                    zd = lq4::ldg_stream_u32(zrow + (gg >> 3));
+                }
+            };
+            load_kb(0, wa, sa, za);
+            load_kb(1, wb, sb, zb);
             for (int kb = 0; kb < num_k; kb++, it++) {
                 const int s = it % kStages;
-                // this k-block's words and group constants are in registers; request the next one's before converting
-                const uint4 wcur = wq;
+                uint4 wcur[kHalves];
+#pragma unroll
+                for (int hh = 0; hh < kHalves; hh++) { wcur[hh] = wa[hh]; wa[hh] = wb[hh]; }
                 const int g = kb >> 1;
-                const uint32_t s16 = sc, zq = (zw >> ((g & 7) * 4)) & 0xFu;
-                if (kb + 1 < num_k) {
-                    wq = lq4::ldg_stream_v4(wrow + (size_t)(kb + 1) * 8);
-                    const int g1 = (kb + 1) >> 1;
-                    if (g1 != g) { sc = lq4::ldg_stream_u16(srow + g1); if ((g1 & 7) == 0) zw = lq4::ldg_stream_u32(zrow + (g1 >> 3)); }
-                }
+                const uint32_t s16 = sa, zq = (za >> ((g & 7) * 4)) & 0xFu;
+                sa = sb; za = zb;
+                load_kb(kb + 2, wb, sb, zb);
                 const uint32_t s2 = s16 | (s16 << 16);
                 const uint32_t zlo = (0x6400u | zq) * 0x10001u;            // (1024 + z, 1024 + z)
                 const uint32_t zhi = (0x5400u | (zq << 4)) * 0x10001u;     // (  64 + z,   64 + z)
                 mbar_wait(empty(s), ((it / kStages) & 1) ^ 1);
                 const uint32_t dst = stage_b(s) + dst_row;
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const uint32_t w = q == 0 ? wcur.x : q == 1 ? wcur.y : q == 2 ? wcur.z : wcur.w;
-                    const uint32_t w8 = w >> 8;
-                    uint32_t h[4];
-                    h[0] = lq4::and_or(w, 0x000F000Fu, 0x64006400u);       // (1024 + q0, 1024 + q4)
-                    h[1] = lq4::and_or(w, 0x00F000F0u, 0x54005400u);       // (  64 + q1,   64 + q5)
-                    h[2] = lq4::and_or(w8, 0x000F000Fu, 0x64006400u);      // q2, q6
-                    h[3] = lq4::and_or(w8, 0x00F000F0u, 0x54005400u);      // q3, q7
+                for (int hh = 0; hh < kHalves; hh++) {
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        __half2 v = *reinterpret_cast<__half2*>(&h[i]);
-                        const uint32_t zz = (i & 1) ? zhi : zlo;
-                        v = __hsub2(v, *reinterpret_cast<const __half2*>(&zz));          // q - z, exact
-                        v = __hmul2(v, *reinterpret_cast<const __half2*>(&s2));          // (q - z) * s, one rounding
-                        h[i] = *reinterpret_cast<uint32_t*>(&v);
+                    for (int q = 0; q < 4; q++) {
+                        const uint32_t w = q == 0 ? wcur[hh].x : q == 1 ? wcur[hh].y : q == 2 ? wcur[hh].z : wcur[hh].w;
+                        const uint32_t w8 = w >> 8;
+                        uint32_t h[4];
+                        h[0] = lq4::and_or(w, 0x000F000Fu, 0x64006400u);       // (1024 + q0, 1024 + q4)
+                        h[1] = lq4::and_or(w, 0x00F000F0u, 0x54005400u);       // (  64 + q1,   64 + q5)
+                        h[2] = lq4::and_or(w8, 0x000F000Fu, 0x64006400u);      // q2, q6
+                        h[3] = lq4::and_or(w8, 0x00F000F0u, 0x54005400u);      // q3, q7
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            __half2 v = *reinterpret_cast<__half2*>(&h[i]);
+                            const uint32_t zz = (i & 1) ? zhi : zlo;
+                            v = __hsub2(v, *reinterpret_cast<const __half2*>(&zz));          // q - z, exact
+                            v = __hmul2(v, *reinterpret_cast<const __half2*>(&s2));          // (q - z) * s, one rounding
+                            h[i] = *reinterpret_cast<uint32_t*>(&v);
+                        }
+                        // k order in memory: (q0,q1) (q2,q3) (q4,q5) (q6,q7)
+                        uint4 o;
+                        o.x = __byte_perm(h[0], h[1], 0x5410); o.y = __byte_perm(h[2], h[3], 0x5410);
+                        o.z = __byte_perm(h[0], h[1], 0x7632); o.w = __byte_perm(h[2], h[3], 0x7632);
+                        const int chunk = (hw0 + hh) * 4 + q;                              // 16-byte chunk of the 128-byte row (8 k each)
+                        lq4::sts_v4_u32(dst + (uint32_t)((chunk ^ (row & 7)) << 4), o);
                     }
-                    // k order in memory: (q0,q1) (q2,q3) (q4,q5) (q6,q7)
-                    uint4 o;
-                    o.x = __byte_perm(h[0], h[1], 0x5410); o.y = __byte_perm(h[2], h[3], 0x5410);
-                    o.z = __byte_perm(h[0], h[1], 0x7632); o.w = __byte_perm(h[2], h[3], 0x7632);
-                    const int chunk = hw * 4 + q;                                      // 16-byte chunk of the 128-byte row (8 k each)
-                    lq4::sts_v4_u32(dst + (uint32_t)((chunk ^ (row & 7)) << 4), o);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> visible to the MMA (async proxy)
                 __syncwarp();
@@ -242,13 +266,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_q4_tc_kernel(const __grid_co
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
             int m_blk, n_blk;
             tile_coord(tile, num_m, num_n, m_blk, n_blk);
-            const int buf = tcount & 1;
-            mbar_wait(tmem_full(buf), (tcount >> 1) & 1);
+            const int buf = tcount % kAccBufs;
+            mbar_wait(tmem_full(buf), (tcount / kAccBufs) & 1);
             tc_fence_after();
 #pragma unroll 1
             for (int half_m = 0; half_m < 2; half_m++) {
                 const int m = m_blk * kBM + half_m * 128 + q4 * 32 + lane;
-                const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * 256 + half_m * 128;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * 256 + half_m * kBN;
 #pragma unroll 1
                 for (int c0 = 0; c0 < kBN; c0 += 32) {
                     uint32_t v[32];
