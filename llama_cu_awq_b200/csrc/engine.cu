@@ -382,60 +382,82 @@ void run_single(Op& op, const int* pPos) {
     launch_interp(pl, nullptr, 1, &op, pPos, -1, false, grid);
 }
 
-// ------------------------------------------------------------------------------- temperature / top-p sampler
-// Off the hot path (the metric is greedy): the reference's pipeline (sampler.h:51-81) restated with the same
-// library calls -- cub::DeviceRadixSort / cub::DeviceScan from the toolkit both builds use -- so that a fixed
-// seed gives the reference's tokens.  All probabilities live in fp16, including the prefix sum.
-__global__ void __launch_bounds__(1024) softmax_logits_kernel(half* logits, int size, float temperature, int* indices) {
-    // gpu_kernels.h:499-550: divide by the temperature (fp16 round trip), softmax in fp16 storage, indices[t] = t
-    const int tid = threadIdx.x, step = blockDim.x;
-    for (int t = tid; t < size; t += step) {
-        indices[t] = t;
-        float val = __half2float(logits[t]);
-        val = __fdiv_rn(val, temperature);
-        logits[t] = __float2half_rn(val);
-    }
+// ------------------------------------------------------------------------------- temperature / top-p sampler (scope row f3)
+// Off the hot path (the metric is greedy).  sampler.h:51-81 is a five-step pipeline over fp16 storage: temperature + softmax,
+// radix sort by probability, inclusive prefix sum, threshold search.  Two of those steps are toolkit library calls
+// (cub::DeviceRadixSort / cub::DeviceScan) and STAY library calls here, for a parity reason that is worth spelling out:
+//   * the prefix sum runs IN FP16 (accumulator type = the half input type).  Its value at every position depends on the
+//     association of the additions, which is cub's tile / warp-scan / look-back structure for this toolkit and architecture --
+//     with ~32000 probabilities of ~3e-5 each the partial sums sit where one fp16 ulp is as large as several addends, so any
+//     other association (a sequential scan, a different tiling) moves the position where the sum crosses `coin * topp` and
+//     therefore the sampled token.  Token parity with the reference for a fixed seed is only defined through the same library.
+//   * the sort only has to be stable and descending on the fp16 key bits (any stable sort gives the same permutation), but
+//     its output feeds the scan above in place, so it is kept beside it.
+// What is ours are the two kernels around the library calls, written for one 1024-thread CTA with the reductions of
+// kernels_sm100.cuh: temperature_softmax_kernel fuses the temperature division, the softmax (fp16 round trips and fp32
+// summation order of gpu_kernels.h:499-550: strided per-thread partial sums, warp trees, warp aggregates added in order) and
+// the index initialisation; threshold_pick_kernel finds the first position whose prefix sum reaches the threshold and
+// publishes token and position like the greedy sampler does.
+constexpr int kSampThreads = 1024;
+
+__device__ __forceinline__ float block_sum_in_order(float v, float* red) {      // cub::BlockReduce<float,1024>::Sum association
+    v = warp_tree_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
-    using BlockReduce = cub::BlockReduce<float, 1024>;
-    __shared__ typename BlockReduce::TempStorage temp;
-    __shared__ float shared_val;
-    float max_val = tid < size ? __half2float(logits[tid]) : -FLT_MAX;
-    for (int i = tid + step; i < size; i += step)
-        if (__half2float(logits[i]) > max_val) max_val = __half2float(logits[i]);
-    max_val = BlockReduce(temp).Reduce(max_val, cub::Max());
-    if (tid == 0) shared_val = max_val;
+    float tot = red[0];
+#pragma unroll
+    for (int w = 1; w < kSampThreads / 32; w++) tot = tot + red[w];
     __syncthreads();
-    max_val = shared_val;
-    float sum = 0.0f;
-    for (int i = tid; i < size; i += step) {
-        const float v = expf(__fsub_rn(__half2float(logits[i]), max_val));
-        logits[i] = __float2half_rn(v);
-        sum = __fadd_rn(sum, v);
-    }
-    __syncthreads();                       // temp is reused
-    sum = BlockReduce(temp).Sum(sum);
-    if (tid == 0) shared_val = sum;
-    __syncthreads();
-    sum = shared_val;
-    for (int t = tid; t < size; t += step) logits[t] = __float2half_rn(__fdiv_rn(__half2float(logits[t]), sum));
+    return tot;
 }
 
-__global__ void __launch_bounds__(1024) sample_top_p_kernel(const half* prefix_sum, const int* indices, int n, float threshold, int* result,
-                                                            volatile int* pPos, int* pPosGpu) {
-    // gpu_kernels.h:555-584: first position whose fp16 prefix sum reaches the threshold (n-1 when none does)
-    const int tid = threadIdx.x, step = blockDim.x;
-    int min_index = n - 1;
-    for (int t = tid; t < n; t += step)
-        if (__half2float(prefix_sum[t]) >= threshold && t < min_index) min_index = t;
-    using BlockReduce = cub::BlockReduce<int, 1024>;
-    __shared__ typename BlockReduce::TempStorage temp;
-    const int min_index_global = BlockReduce(temp).Reduce(min_index, cub::Min());
+__global__ void __launch_bounds__(kSampThreads) temperature_softmax_kernel(half* probs, int n, float temperature, int* indices) {
+    __shared__ float red[kSampThreads / 32];
+    const int tid = threadIdx.x;
+    // pass 1: logits / temperature, stored back in fp16 (the reference's round trip), running maximum of the rounded values
+    float mx = -FLT_MAX;
+    for (int i = tid; i < n; i += kSampThreads) {
+        const half h = __float2half_rn(__fdiv_rn(__half2float(probs[i]), temperature));
+        probs[i] = h;
+        indices[i] = i;
+        mx = fmaxf(mx, __half2float(h));
+    }
+    mx = warp_max(mx);
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int w = 1; w < kSampThreads / 32; w++) mx = fmaxf(mx, red[w]);
+    __syncthreads();
+    // pass 2: exp(x - max) parked in fp16, the sum adds the unrounded values (per-thread strided order, then the cub tree)
+    float part = 0.0f;
+    for (int i = tid; i < n; i += kSampThreads) {
+        const float e = expf(__fsub_rn(__half2float(probs[i]), mx));
+        probs[i] = __float2half_rn(e);
+        part = __fadd_rn(part, e);
+    }
+    const float total = block_sum_in_order(part, red);
+    // pass 3: normalise the fp16-rounded exponentials
+    for (int i = tid; i < n; i += kSampThreads) probs[i] = __float2half_rn(__fdiv_rn(__half2float(probs[i]), total));
+}
+
+__global__ void __launch_bounds__(kSampThreads) threshold_pick_kernel(const half* prefix, const int* indices, int n, float threshold, int* tokens,
+                                                                      volatile int* pos_host, int* pos_dev) {
+    __shared__ int first[kSampThreads / 32];
+    const int tid = threadIdx.x;
+    int best = n - 1;                                   // nothing reaches the threshold: the last entry (gpu_kernels.h:559)
+    for (int i = tid; i < n && i < best; i += kSampThreads)
+        if (__half2float(prefix[i]) >= threshold) { best = i; break; }      // a thread's positions ascend: its first hit is its minimum
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((tid & 31) == 0) first[tid >> 5] = best;
+    __syncthreads();
     if (tid == 0) {
-        int token_pos = *pPos;
-        token_pos++;
-        result[token_pos] = indices[min_index_global];
-        *pPos = token_pos;
-        *pPosGpu = token_pos;
+        for (int w = 1; w < kSampThreads / 32; w++) best = min(best, first[w]);
+        const int next_pos = *pos_host + 1;
+        tokens[next_pos] = indices[best];
+        *pos_host = next_pos;
+        *pos_dev = next_pos;
     }
 }
 
@@ -893,7 +915,7 @@ static bool is_greedy(const Sampler* sampler, int gen_token) { return sampler->t
 // the non-greedy branch of sample() (sampler.h:51-80) with an already drawn coin
 static void sample_nongreedy(Sampler* sampler, RunState* s, float coin, cudaStream_t st) {
     const int n = sampler->vocab_size;
-    softmax_logits_kernel<<<1, 1024, 0, st>>>(s->logits, n, sampler->temperature, sampler->indices);
+    temperature_softmax_kernel<<<1, kSampThreads, 0, st>>>(s->logits, n, sampler->temperature, sampler->indices);
     float threshold = 0.0f;
     if (sampler->topp <= 0 || sampler->topp >= 1) {
         threshold = coin;
@@ -912,7 +934,7 @@ static void sample_nongreedy(Sampler* sampler, RunState* s, float coin, cudaStre
         LQ4_CHECK(cudaMalloc(&sampler->tempStorage_scan, sampler->temp_storage_bytes_scan));
     }
     cub::DeviceScan::InclusiveSum(sampler->tempStorage_scan, sampler->temp_storage_bytes_scan, s->logits, s->logits, n, st);
-    sample_top_p_kernel<<<1, 1024, 0, st>>>(s->logits, sampler->indices, n, threshold, &(s->shared_data->tokens[0]), &(s->shared_data->pos), s->pos);
+    threshold_pick_kernel<<<1, kSampThreads, 0, st>>>(s->logits, sampler->indices, n, threshold, &(s->shared_data->tokens[0]), &(s->shared_data->pos), s->pos);
 }
 
 void lq4_sample(Sampler* sampler, RunState* s, int gen_token, void* cuda_stream) {

@@ -1215,15 +1215,22 @@ __device__ void run_attn_t(Ctx& c, const Op& op, bool prefetched) {
             named_bar(kBarAll, nt);                        // tile ti is complete for everyone (first time round also qs / krow / vrow); tile ti-1 is no longer read
             attn_tile_async(c, kbase, op.kv_stride, hs, op.max_seq, ti + kAttnAhead, pos);     // into the buffer tile ti-1 just left
             const uint32_t kbuf = attn_tile_buf(c, hs, op.max_seq, ti);
-#pragma unroll 2
-            for (int r = warp; r < nrows; r += c.nwc) {
-                const uint32_t row = kbuf + (uint32_t)r * hs * 2;
-                float sum = 0.0f;
+            // four rows per warp and pass: their lane chains are independent, and one 6-shuffle transposing tree (the cub
+            // association per row, see warp_tree_sum4) replaces four 5-shuffle trees
+#pragma unroll 1
+            for (int r0 = warp * 4; r0 < nrows; r0 += c.nwc * 4) {
+                float s4[4];
 #pragma unroll
-                for (int i = 0; i < NS; i++) sum = __fmaf_rn(h2f_bits(lds_u16(row + (i * 32 + lane) * 2)), qs[i * 32 + lane], sum);
-                sum = warp_tree_sum(sum);
-                sum = __fmul_rn(sum, op.att_alpha);
-                if (lane == 0) att[tile0 + r] = __half2float(__float2half_rn(sum));
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t row = kbuf + (uint32_t)min(r0 + q, nrows - 1) * hs * 2;
+                    float sum = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < NS; i++) sum = __fmaf_rn(h2f_bits(lds_u16(row + (i * 32 + lane) * 2)), qs[i * 32 + lane], sum);
+                    s4[q] = sum;
+                }
+                const float tot = __fmul_rn(warp_tree_sum4(s4[0], s4[1], s4[2], s4[3], lane), op.att_alpha);
+                const int rq = r0 + 2 * (lane & 1) + ((lane >> 1) & 1);      // lanes 0,1,2,3 hold rows r0 + 0,2,1,3
+                if (lane < 4 && rq < nrows) att[tile0 + rq] = __half2float(__float2half_rn(tot));
             }
         }
         named_bar(kBarAll, nt);                            // all tile reads done; krow visible even when no tile loop ran (pos == 0)
