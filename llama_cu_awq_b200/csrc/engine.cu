@@ -51,6 +51,8 @@ struct NetPlan {
     Op* d_ops = nullptr;
     int nops = 0;              // including the trailing OP_ARGMAX
     uint32_t* tagged = nullptr;   // flag-in-data activation vectors of the fused step: x | xb | hb | q | k (un-rotated) | v | argmax candidates
+    uint16_t* att_sc = nullptr;   // split attention: [heads of this rank][seq_len] fp16 scores
+    unsigned* att_flags = nullptr;
     uint32_t* peers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // every rank's `tagged`, mapped here
     int world = 1, rank = 0;
     unsigned seq_base = 0;        // activation-tag base of the last launch of this plan
@@ -82,6 +84,11 @@ struct Engine {
     unsigned long long* trace = nullptr;
     int trace_n = 0;
     std::map<const void*, void*> arenas;   // Transformer* -> device arena (loader)
+    uint16_t* att_sc = nullptr;            // operator API: score exchange of the split attention (grown on demand)
+    size_t att_sc_elems = 0;
+    unsigned* att_flags = nullptr;         // [heads][4], zero-initialised once
+    int att_flag_heads = 0;
+    unsigned op_seq = 0;                   // single-op launches: a fresh Ctx::op_seq base per launch
     char err[512] = {0};
 };
 Engine g;
@@ -319,7 +326,8 @@ void launch_interp(const Plan& pl, const Op* d_ops, int nops, const Op* one, con
     // Activation tags: consecutive launches over the same buffers must never share a tag.  Each plan advances its own base by
     // its op count per launch, so two consecutive launches differ by nops (mod 2^15), whatever else ran in between; all ranks
     // of a tensor-parallel group launch in lockstep and therefore agree on it.
-    P.seq_base = 0;
+    g.op_seq = (g.op_seq + 1u) & 0x3FFFFFFFu;
+    P.seq_base = g.op_seq;        // single-op launches: only Ctx::op_seq (split-attention flags) depends on it
     if (tp_or_plan != nullptr) {
         NetPlan* np = const_cast<NetPlan*>(tp_or_plan);
         np->seq_base = (np->seq_base + (unsigned)np->nops) & 0x3FFFFFFFu;
@@ -370,7 +378,18 @@ void run_single(Op& op, const int* pPos) {
         xs = op_xs_bytes(op);
         meta = op_meta_bytes(op, grid);
     } else if (op.kind == OP_ATTN) {
-        grid = std::min(g.sm_count, op.n_heads);
+        // long contexts run 2 or 4 CTAs per head (interp_sm100.cuh, run_attn_split): scratch for the score exchange, grown on demand
+        const size_t need = (size_t)op.n_heads * op.max_seq;
+        if (g.att_sc_elems < need || g.att_flag_heads < op.n_heads) {
+            LQ4_CHECK(cudaStreamSynchronize(g.stream));
+            cudaFree(g.att_sc); cudaFree(g.att_flags);
+            g.att_sc_elems = std::max(need, g.att_sc_elems); g.att_flag_heads = std::max(op.n_heads, g.att_flag_heads);
+            LQ4_CHECK(cudaMalloc((void**)&g.att_sc, g.att_sc_elems * sizeof(uint16_t)));
+            LQ4_CHECK(cudaMalloc((void**)&g.att_flags, (size_t)g.att_flag_heads * 4 * sizeof(unsigned)));
+            LQ4_CHECK(cudaMemset(g.att_flags, 0, (size_t)g.att_flag_heads * 4 * sizeof(unsigned)));
+        }
+        op.att_split = 4; op.att_sc = g.att_sc; op.att_sc_stride = op.max_seq; op.att_flags = g.att_flags;
+        grid = std::min(g.sm_count, op.n_heads * op.att_split);
         xs = attn_scratch_bytes(op.head_size, op.max_seq);
     } else {
         grid = 1;
@@ -500,7 +519,7 @@ const char* lq4_last_error(void) { return g.err; }
 int lq4_sm_count(void) { ensure_init(); return g.sm_count; }
 
 static void drop_net_plans() {
-    for (auto& kv : g.nets) { cudaFree(kv.second.d_ops); cudaFree(kv.second.tagged); }
+    for (auto& kv : g.nets) { cudaFree(kv.second.d_ops); cudaFree(kv.second.tagged); cudaFree(kv.second.att_sc); cudaFree(kv.second.att_flags); }
     g.nets.clear();
 }
 
@@ -715,7 +734,7 @@ static NetPlan& get_net_plan(Config* p, RunState* s, TransformerWeights* w) {
     memcpy(key.data() + sizeof(Config) + sizeof(RunState), w, sizeof(TransformerWeights));
     NetPlan& np = g.nets[(const void*)s];
     if (np.key == key) return np;
-    if (np.d_ops) { LQ4_CHECK(cudaStreamSynchronize(g.stream)); cudaFree(np.d_ops); cudaFree(np.tagged); np.d_ops = nullptr; np.tagged = nullptr; }
+    if (np.d_ops) { LQ4_CHECK(cudaStreamSynchronize(g.stream)); cudaFree(np.d_ops); cudaFree(np.tagged); cudaFree(np.att_sc); cudaFree(np.att_flags); np.d_ops = nullptr; np.tagged = nullptr; np.att_sc = nullptr; np.att_flags = nullptr; }
     np.key = key;
     np.ok = false;
 
@@ -752,6 +771,10 @@ static NetPlan& get_net_plan(Config* p, RunState* s, TransformerWeights* w) {
     uint32_t* vrawt = krawt + kv_dim;
     uint32_t* cand = vrawt + kv_dim;
     const float2* rope_tab = rope_table(p->rope_theta, head_size, p->seq_len);
+    // split attention (long contexts): fp16 score exchange + per-part flags for this rank's heads
+    LQ4_CHECK(cudaMalloc((void**)&np.att_sc, (size_t)sheads * p->seq_len * sizeof(uint16_t)));
+    LQ4_CHECK(cudaMalloc((void**)&np.att_flags, (size_t)sheads * 4 * sizeof(unsigned)));
+    LQ4_CHECK(cudaMemset(np.att_flags, 0, (size_t)sheads * 4 * sizeof(unsigned)));
 
     std::vector<Op> ops;
     bool ok = true;
@@ -782,6 +805,7 @@ static NetPlan& get_net_plan(Config* p, RunState* s, TransformerWeights* w) {
             // run_transformer's graph bins (llama2_q4.cu:354-360) hand MultiHeadAttention a max_seq_len above 8192 exactly when
             // pos + 1 > 8192 (bins are 128 ... 8192, then the model's seq_len): the softmax variant depends on the position only
             op.exp16_from = MAX_SEQ_LEN_SMEM_KERNEL;
+            op.att_split = 4; op.att_sc = np.att_sc; op.att_sc_stride = p->seq_len; op.att_flags = np.att_flags;
             op.qt = qt + R * sdim; op.krawt = krawt + R * skv; op.vrawt = vrawt + R * skv;
             op.attn_out32 = xbt + R * sdim; op.attn_bcast = bc; op.rope_tab = rope_tab;
             ops.push_back(op);
@@ -1104,7 +1128,7 @@ void lq4_free_transformer(Transformer* t) {
     if (np != g.nets.end()) {
         for (int r = 0; r < np->second.world; r++)
             if (r != np->second.rank && np->second.peers[r] != nullptr) cudaIpcCloseMemHandle(np->second.peers[r]);
-        cudaFree(np->second.d_ops); cudaFree(np->second.tagged); g.nets.erase(np);
+        cudaFree(np->second.d_ops); cudaFree(np->second.tagged); cudaFree(np->second.att_sc); cudaFree(np->second.att_flags); g.nets.erase(np);
     }
     cudaFree(s->x); cudaFree(s->xb); cudaFree(s->pos); cudaFree(s->hb); cudaFree(s->q); cudaFree(s->att);
     cudaFree(s->logits); cudaFree(s->key_cache); cudaFree(s->value_cache); cudaFreeHost(s->shared_data);

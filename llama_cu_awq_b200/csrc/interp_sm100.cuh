@@ -103,6 +103,10 @@ struct Op {
     const float2* rope_tab;
     int n_heads, head_size, kv_mul, kv_stride, max_seq;
     int exp16_from;        // softmax over more than this many positions uses the arithmetic of softmax_kernel_no_smem (gpu_kernels.h:403-446)
+    int att_split;         // long contexts: CTAs per head (1, 2 or 4; needs att_sc / att_flags and n_heads * att_split CTAs), see run_attn_split
+    int att_sc_stride;     // elements per head of att_sc
+    uint16_t* att_sc;      // [n_heads][att_sc_stride] fp16 scores exchanged between the CTAs of a head
+    unsigned* att_flags;   // [n_heads][4] "my scores are written" flags of the parts (value: Ctx::op_seq)
     float att_alpha;
     // OP_ARGMAX
     const half* logits;
@@ -503,6 +507,7 @@ struct Ctx {
     int meta_pending;         // scale/zero buffer to hand back to the producer once every warp has left the op, or -1
     unsigned nsync;           // grid barriers taken so far
     uint32_t tag_in, tag_out; // activation tags: of the op whose output this op reads, and of this op
+    unsigned op_seq;          // launch counter * nops + op index + 1: unique per (launch, op) for 2^30 ops (split-attention flags)
     unsigned long long* tr;   // detailed phase trace of the current op (this CTA's 8 entries) or nullptr
 };
 __device__ __forceinline__ void cyc_mark(const Ctx& c, int k) {      // SM clock, warp 0 lane 0: sub-microsecond phases
@@ -1133,8 +1138,26 @@ __device__ __forceinline__ void attn_tile_async(const Ctx& c, const half* base, 
     }
     cp_async_commit();
 }
+__device__ __forceinline__ int attn_parts(const Op& op, int pos, int grid);
+__device__ __forceinline__ void attn_rows_async(const Ctx& c, uint32_t dst, const half* src, int stride_elems, int row_bytes, int nrows);
 __device__ void attn_prefetch(const Ctx& c, const Op& op) {
-    const int h = blockIdx.x, hs = op.head_size;
+    const int hs = op.head_size;
+    const int S = attn_parts(op, c.pos, (int)gridDim.x);
+    if (S > 1) {                                    // split mode: my K tiles are part_id, part_id + S, ... of head blockIdx.x / S
+        const int h = blockIdx.x / S, part_id = blockIdx.x - h * S;
+        if (h >= op.n_heads) return;
+        const half* kb = op.kcache + (size_t)(h / op.kv_mul) * hs;
+        const int ntiles = (c.pos + kAttnTile - 1) / kAttnTile;
+        const uint32_t bufs = c.sm.xs + attn_fixed_bytes(hs, op.max_seq);
+        for (int m = 0; m < kAttnAhead; m++) {
+            const int ti = part_id + m * S;
+            int nrows = (ti < ntiles) ? c.pos - ti * kAttnTile : 0;
+            if (nrows > kAttnTile) nrows = kAttnTile;
+            attn_rows_async(c, bufs + (uint32_t)m * (kAttnTile * hs * 2), kb + (size_t)ti * kAttnTile * op.kv_stride, op.kv_stride, hs * 2, nrows);
+        }
+        return;
+    }
+    const int h = blockIdx.x;
     if (h >= op.n_heads) return;
     const half* kb = op.kcache + (size_t)(h / op.kv_mul) * hs;
     for (int ti = 0; ti < kAttnAhead; ti++) attn_tile_async(c, kb, op.kv_stride, hs, op.max_seq, ti, c.pos);
@@ -1338,7 +1361,274 @@ __device__ void run_attn_t(Ctx& c, const Op& op, bool prefetched) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Long contexts: S = 2 or 4 CTAs per head ("parts").  One CTA per head keeps 24 KB of K / V tiles in flight, which bounds a
+// 1024-position head at ~35 us; S parts stream S times as much.
+//   scores   part c takes the K tiles ti = c, c + S, ... (and part 0 the row of this step), rounds each score to fp16 like
+//            the reference and writes it to att_sc[h][t]; a release store of Ctx::op_seq to att_flags[h][c] publishes them
+//   softmax  every part waits for all S flags, reads ALL scores of the head and runs the same softmax (identical bits)
+//   PV       part c owns the output dimensions [c * hs/S, (c+1) * hs/S): it streams that slice of every V row (S * 32 rows
+//            per tile buffer) and keeps the reference's chains (lane tx over t = 32 e + tx, e ascending) and its 32-way tree
+// Everything a part computes is a chain or tree of the reference in the reference's order: results are bit-identical to
+// the one-CTA path.
+// ------------------------------------------------------------------------------------------------
+constexpr int kAttnSplitFrom = 384;     // positions from which the split pays for its extra exchange (~2 us)
+__device__ __forceinline__ int attn_parts(const Op& op, int pos, int grid) {
+    if (pos < kAttnSplitFrom || op.att_sc == nullptr || (op.rope_tab != nullptr && op.qt == nullptr)) return 1;
+    int S = op.att_split;
+    while (S > 1 && (op.n_heads * S > grid || (op.head_size / 32) % S)) S >>= 1;
+    return S;
+}
+// rows [row0, row0 + nrows) x `row_bytes` (a multiple of 16) of a strided global matrix -> contiguous shared memory; closes a copy group
+__device__ __forceinline__ void attn_rows_async(const Ctx& c, uint32_t dst, const half* src, int stride_elems, int row_bytes, int nrows) {
+    if (nrows > 0) {
+        const int vpr = row_bytes >> 4, total = nrows * vpr;
+        for (int idx = c.ctid; idx < total; idx += c.nthreads) {
+            const int r = idx / vpr, v = idx - r * vpr;
+            cp_async16(dst + r * row_bytes + v * 16, src + (size_t)r * stride_elems + v * 8);
+        }
+    }
+    cp_async_commit();
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int NSER, int S>
+__device__ void run_attn_split(Ctx& c, const Op& op, bool prefetched) {
+    constexpr int NS = NSER;                               // hs / 32
+    constexpr int NSP = NS / S;                            // output dimensions per lane in the PV phase
+    const int hs = op.head_size, nt = c.nthreads, tid = c.ctid, lane = c.lane, warp = c.warp;
+    const int h = blockIdx.x / S, part_id = blockIdx.x - h * S;
+    if (h >= op.n_heads) return;
+    float* qs = reinterpret_cast<float*>(c.scratch);
+    float* krow = qs + hs;
+    float* vrow = krow + hs;
+    float* att = vrow + hs;
+    float* part = reinterpret_cast<float*>(c.scratch + attn_fixed_bytes(hs, op.max_seq));
+    float* red = c.red;
+    const int pos = c.pos, size = pos + 1;
+    const int kvh = h / op.kv_mul;
+    half* kbase = op.kcache + (size_t)kvh * hs;
+    const half* vbase = op.vcache + (size_t)kvh * hs;
+    const int ntiles = (pos + kAttnTile - 1) / kAttnTile;
+    const int mtiles = (ntiles > part_id) ? (ntiles - part_id + S - 1) / S : 0;      // my K tiles: part_id, part_id + S, ...
+    const uint32_t bufs = c.sm.xs + attn_fixed_bytes(hs, op.max_seq);
+    const int tile_bytes = kAttnTile * hs * 2;
+    auto k_tile_async = [&](int m) {
+        const int ti = part_id + m * S;
+        int nrows = (m < mtiles) ? pos - ti * kAttnTile : 0;
+        if (nrows > kAttnTile) nrows = kAttnTile;
+        attn_rows_async(c, bufs + (uint32_t)(m & kAttnAhead) * tile_bytes, kbase + (size_t)ti * kAttnTile * op.kv_stride, op.kv_stride, hs * 2, nrows);
+    };
+    if (!prefetched)
+        for (int m = 0; m < kAttnAhead; m++) k_tile_async(m);
+    // ---- q, the new k row (rotated) and the new v row -> shared memory (every part; part 0 of the first head of a kv group stores k) ----
+    if (op.rope_tab != nullptr) {
+        for (int i = tid; i < hs / 2; i += nt) {
+            const float2 cs = op.rope_tab[(size_t)pos * (hs / 2) + i];
+            half* q = op.q + (size_t)h * hs;
+            const half* kr = op.kraw + (size_t)kvh * hs;
+            uint32_t q0b, q1b, k0b, k1b;
+            if (op.qt != nullptr) {
+                const uint32_t* pq = op.qt + (size_t)h * hs + i;
+                const uint32_t* pk = op.krawt + (size_t)kvh * hs + i;
+                const uint32_t tag = c.tag_in;
+                const unsigned long long t0 = global_ns();
+                for (;;) {
+                    q0b = ld_tagged_any(pq); q1b = ld_tagged_any(pq + hs / 2); k0b = ld_tagged_any(pk); k1b = ld_tagged_any(pk + hs / 2);
+                    if (((q0b >> 16) == tag) & ((q1b >> 16) == tag) & ((k0b >> 16) == tag) & ((k1b >> 16) == tag)) break;
+                    if (global_ns() - t0 > kWaitLimitNs) asm volatile("trap;");
+                }
+                q0b &= 0xFFFFu; q1b &= 0xFFFFu; k0b &= 0xFFFFu; k1b &= 0xFFFFu;
+            } else {
+                q0b = ld_cg_u16(q + i); q1b = ld_cg_u16(q + i + hs / 2); k0b = ld_cg_u16(kr + i); k1b = ld_cg_u16(kr + i + hs / 2);
+            }
+            const float q0 = h2f_bits(q0b), q1 = h2f_bits(q1b), k0 = h2f_bits(k0b), k1 = h2f_bits(k1b);
+            const half o0 = __float2half_rn(__fmaf_rn(q0, cs.x, -__fmul_rn(q1, cs.y)));
+            const half o1 = __float2half_rn(__fmaf_rn(q1, cs.x, __fmul_rn(q0, cs.y)));
+            (void)q;      // the in-place rotation of q (operator-API semantics) is left to the one-CTA path: other parts still read q here
+            qs[i] = __half2float(o0); qs[i + hs / 2] = __half2float(o1);
+            const half r0 = __float2half_rn(__fmaf_rn(k0, cs.x, -__fmul_rn(k1, cs.y)));
+            const half r1 = __float2half_rn(__fmaf_rn(k0, cs.y, __fmul_rn(k1, cs.x)));
+            krow[i] = __half2float(r0); krow[i + hs / 2] = __half2float(r1);
+            if (h == kvh * op.kv_mul && part_id == 0) {
+                half* kd = kbase + (size_t)pos * op.kv_stride;
+                kd[i] = r0; kd[i + hs / 2] = r1;
+            }
+        }
+    } else {
+        for (int i = tid; i < hs; i += nt) {
+            qs[i] = h2f_bits(ld_cg_u16(op.q + (size_t)h * hs + i));
+            krow[i] = h2f_bits(ld_cg_u16(kbase + (size_t)pos * op.kv_stride + i));
+        }
+    }
+    for (int i = tid; i < hs; i += nt)
+        vrow[i] = h2f_bits(op.vrawt != nullptr ? poll1(op.vrawt + (size_t)kvh * hs + i, c.tag_in) : ld_cg_u16(vbase + (size_t)pos * op.kv_stride + i));
+    // ---- my share of the scores ----
+    uint16_t* sc = op.att_sc + (size_t)h * op.att_sc_stride;
+#pragma unroll 1
+    for (int m = 0; m < mtiles; m++) {
+        const int tile0 = (part_id + m * S) * kAttnTile, nrows = (pos - tile0 < kAttnTile) ? pos - tile0 : kAttnTile;
+        cp_async_wait<kAttnAhead - 1>();
+        named_bar(kBarAll, nt);
+        k_tile_async(m + kAttnAhead);
+        const uint32_t kbuf = bufs + (uint32_t)(m & kAttnAhead) * tile_bytes;
+#pragma unroll 1
+        for (int r0 = warp * 4; r0 < nrows; r0 += c.nwc * 4) {
+            float s4[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint32_t row = kbuf + (uint32_t)min(r0 + q, nrows - 1) * hs * 2;
+                float sum = 0.0f;
+#pragma unroll
+                for (int i = 0; i < NS; i++) sum = __fmaf_rn(h2f_bits(lds_u16(row + (i * 32 + lane) * 2)), qs[i * 32 + lane], sum);
+                s4[q] = sum;
+            }
+            const float tot = __fmul_rn(warp_tree_sum4(s4[0], s4[1], s4[2], s4[3], lane), op.att_alpha);
+            const int rq = r0 + 2 * (lane & 1) + ((lane >> 1) & 1);
+            if (lane < 4 && rq < nrows) sc[tile0 + rq] = (uint16_t)f2h_bits(tot);
+        }
+    }
+    named_bar(kBarAll, nt);                                // qs / krow visible even when this part had no tile; all tile reads done
+    if (part_id == 0 && warp == 0) {                       // the row of this step
+        float sum = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NS; i++) sum = __fmaf_rn(krow[i * 32 + lane], qs[i * 32 + lane], sum);
+        sum = warp_tree_sum(sum);
+        sum = __fmul_rn(sum, op.att_alpha);
+        if (lane == 0) sc[pos] = (uint16_t)f2h_bits(sum);
+    }
+    // the first V slices travel while the scores are exchanged: K is dead from here on
+    cp_async_wait<0>();
+    const int dsub = hs / S, vrow_bytes = dsub * 2, rows_per_buf = kAttnTile * S;      // S * 32 rows x (hs / S) dims = one tile buffer
+    const int nst = (pos + rows_per_buf - 1) / rows_per_buf;
+    auto v_tile_async = [&](int sti) {
+        int nrows = (sti < nst) ? pos - sti * rows_per_buf : 0;
+        if (nrows > rows_per_buf) nrows = rows_per_buf;
+        attn_rows_async(c, bufs + (uint32_t)(sti & kAttnAhead) * tile_bytes, vbase + (size_t)sti * rows_per_buf * op.kv_stride + part_id * dsub, op.kv_stride,
+                        vrow_bytes, nrows);
+    };
+    named_bar(kBarAll, nt);                                // every thread's score stores precede the release below; K buffers are free
+    for (int sti = 0; sti < kAttnAhead; sti++) v_tile_async(sti);
+    if (tid == 0) st_release_u32(op.att_flags + h * 4 + part_id, c.op_seq);
+    if (tid < S) {
+        const unsigned* f = op.att_flags + h * 4 + tid;
+        if (ld_acquire_u32(f) != c.op_seq) {
+            const unsigned long long t0 = global_ns();
+            while (ld_acquire_u32(f) != c.op_seq)
+                if (global_ns() - t0 > kWaitLimitNs) asm volatile("trap;");
+        }
+    }
+    named_bar(kBarAll, nt);
+    trace_mark(c, 3);
+    for (int i = tid; i < size; i += nt) att[i] = h2f_bits(ld_cg_u16(sc + i));
+    named_bar(kBarAll, nt);
+    // ---- softmax: the same code path as the one-CTA kernel, run by every part ----
+    const bool exp16 = size > op.exp16_from;
+    float mx = (size < 1024) ? 0.0f : -INFINITY;
+    for (int i = tid; i < size; i += nt) mx = fmaxf(mx, att[i]);
+    mx = warp_max(mx);
+    if (lane == 0) red[32 + warp] = mx;
+    named_bar(kBarAll, nt);
+    mx = red[32];
+    for (int w = 1; w < c.nwc; w++) mx = fmaxf(mx, red[32 + w]);
+    for (int vw = warp; vw < 32; vw += c.nwc) {
+        const int vt = vw * 32 + lane;
+        float ssum = 0.0f;
+        for (int i = vt; i < size; i += 1024) {
+            const float e = expf(__fsub_rn(att[i], mx));
+            att[i] = exp16 ? __half2float(__float2half_rn(e)) : e;
+            ssum = __fadd_rn(ssum, e);
+        }
+        ssum = warp_tree_sum(ssum);
+        if (lane == 0) red[vw] = ssum;
+    }
+    named_bar(kBarAll, nt);
+    float tot = red[0];
+#pragma unroll
+    for (int w = 1; w < 32; w++) tot = tot + red[w];
+    for (int i = tid; i < size; i += nt) {
+        const __half pr = __float2half_rn(__fdiv_rn(att[i], tot));
+        att[i] = __half2float(pr);
+        if (op.att_out != nullptr && part_id == 0) op.att_out[(size_t)h * size + i] = pr;
+    }
+    named_bar(kBarAll, nt);
+    trace_mark(c, 4);
+    // ---- PV over my output dimensions: lane owns NS / S consecutive ones; chains as in the one-CTA kernel ----
+    float a[4][NSP];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int q = 0; q < NSP; q++) a[k][q] = 0.0f;
+#pragma unroll 1
+    for (int sti = 0; sti < nst; sti++) {
+        const int tile0 = sti * rows_per_buf, nrows = (pos - tile0 < rows_per_buf) ? pos - tile0 : rows_per_buf;
+        cp_async_wait<kAttnAhead - 1>();
+        named_bar(kBarAll, nt);
+        v_tile_async(sti + kAttnAhead);
+        const uint32_t buf = bufs + (uint32_t)(sti & kAttnAhead) * tile_bytes;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int tx = warp + k * c.nwc;
+            if (tx < 32) {
+#pragma unroll
+                for (int es = 0; es < S; es++) {
+                    const int r = es * 32 + tx;
+                    if (r < nrows) {
+                        const float pt = att[tile0 + r];
+                        const uint32_t row = buf + (uint32_t)r * vrow_bytes + lane * NSP * 2;
+#pragma unroll
+                        for (int q = 0; q < NSP; q++) a[k][q] = __fmaf_rn(h2f_bits(lds_u16(row + q * 2)), pt, a[k][q]);
+                    }
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+    named_bar(kBarAll, nt);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int tx = warp + k * c.nwc;
+        if (tx < 32) {
+            if ((pos & 31) == tx) {
+                const float pt = att[pos];
+#pragma unroll
+                for (int q = 0; q < NSP; q++) a[k][q] = __fmaf_rn(vrow[part_id * dsub + lane * NSP + q], pt, a[k][q]);
+            }
+#pragma unroll
+            for (int q = 0; q < NSP; q++) part[tx * dsub + lane * NSP + q] = a[k][q];
+        }
+    }
+    named_bar(kBarAll, nt);
+    trace_mark(c, 6);
+    for (int i = tid; i < dsub; i += nt) {
+        float v[32];
+#pragma unroll
+        for (int w = 0; w < 32; w++) v[w] = part[w * dsub + i];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+#pragma unroll
+            for (int w = 0; w < 32; w += 2 * o) v[w] = v[w] + v[w + o];
+        const size_t e = (size_t)h * hs + part_id * dsub + i;
+        if (op.attn_out32 != nullptr) st_tagged_maybe_all(*c.P, op.attn_bcast != 0, op.attn_out32 + e, c.tag_out, f2h_bits(v[0]));
+        else op.attn_out[e] = __float2half_rn(v[0]);
+    }
+    named_bar(kBarAll, nt);
+    trace_mark(c, 7);
+}
+
 __device__ void run_attn(Ctx& c, const Op& op, bool prefetched) {
+    const int S = attn_parts(op, c.pos, (int)gridDim.x);
+    if (S > 1) {      // attn_parts admits S > 1 only when (hs / 32) % S == 0
+        if (op.head_size == 128 && S == 4) run_attn_split<4, 4>(c, op, prefetched);
+        else if (op.head_size == 128) run_attn_split<4, 2>(c, op, prefetched);
+        else run_attn_split<2, 2>(c, op, prefetched);
+        return;
+    }
     switch (op.head_size) {            // the host accepts only these head sizes for the persistent kernel
         case 128: run_attn_t<4>(c, op, prefetched); break;
         case 64: run_attn_t<2>(c, op, prefetched); break;
@@ -1455,7 +1745,7 @@ __global__ void __launch_bounds__(32 * (kMaxConsumerWarps + 1), 1) interp_kernel
     c.nwc = P.nwc; c.nthreads = P.nwc * 32; c.warp = warp; c.lane = lane; c.ctid = threadIdx.x;
     c.pos = (P.pPos != nullptr) ? *P.pPos : 0;
     c.token = (P.tokens != nullptr) ? P.tokens[c.pos] : 0;
-    c.qbase = 0; c.qtotal = 0; c.mcount = 0; c.meta_pending = -1; c.nsync = 0; c.tr = nullptr; c.tag_in = c.tag_out = 0;
+    c.qbase = 0; c.qtotal = 0; c.mcount = 0; c.meta_pending = -1; c.nsync = 0; c.tr = nullptr; c.tag_in = c.tag_out = 0; c.op_seq = 0;
 
     const Op& op = *reinterpret_cast<const Op*>(smem + kOpOffset);
     for (int o = 0; o < P.nops; o++) {
@@ -1474,6 +1764,7 @@ __global__ void __launch_bounds__(32 * (kMaxConsumerWarps + 1), 1) interp_kernel
             if (sync_before) grid_arrive(P.sync);
         }
         c.meta_pending = -1;
+        c.op_seq = ((P.seq_base + (unsigned)o) & 0x3FFFFFFFu) + 1u;
         c.tag_out = ((P.seq_base + (unsigned)o + 1u) & 0x7FFFu) | 0x8000u;     // never 0: a zeroed buffer is never "fresh"
         c.tag_in = ((P.seq_base + (unsigned)o) & 0x7FFFu) | 0x8000u;           // the previous op's
         const bool attn_pref = (ops[o].kind == OP_ATTN);
