@@ -134,7 +134,8 @@ void ensure_init() {
     if ((env = getenv("LQ4_SLOT_BYTES"))) g.opt_slot_bytes = atoi(env);
     LQ4_CHECK(cudaMalloc((void**)&g.sync, 2 * sizeof(unsigned)));
     LQ4_CHECK(cudaMemset(g.sync, 0, 2 * sizeof(unsigned)));
-    LQ4_CHECK(cudaFuncSetAttribute(interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g.max_smem));
+    LQ4_CHECK(cudaFuncSetAttribute(interp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.max_smem));
+    LQ4_CHECK(cudaFuncSetAttribute(interp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.max_smem));
     g.inited = true;
 }
 
@@ -315,8 +316,10 @@ QWeight slice_cols(const QWeight& w, int K, int c0) {
     return r;
 }
 
+// long_ctx: launch the kernel instance that can split a head's attention over several CTAs (positions >= kAttnSplitFrom).  Both
+// instances give bit-identical results at every position, so a host that only knows a bound of the position may pick either.
 void launch_interp(const Plan& pl, const Op* d_ops, int nops, const Op* one, const int* pPos, int write_token,
-                   bool cooperative, int grid, const NetPlan* tp_or_plan = nullptr) {
+                   bool cooperative, int grid, const NetPlan* tp_or_plan = nullptr, bool long_ctx = false) {
     InterpParams P;
     memset(&P, 0, sizeof P);
     P.ops = d_ops; P.nops = nops;
@@ -363,7 +366,7 @@ void launch_interp(const Plan& pl, const Op* d_ops, int nops, const Op* one, con
         cfg.attrs = attr;
         cfg.numAttrs = 1;
     }
-    cudaError_t e = cudaLaunchKernelEx(&cfg, interp_kernel, P);
+    cudaError_t e = long_ctx ? cudaLaunchKernelEx(&cfg, interp_kernel<true>, P) : cudaLaunchKernelEx(&cfg, interp_kernel<false>, P);
     if (e != cudaSuccess) { set_err("interp_kernel launch", e); exit(EXIT_FAILURE); }
 }
 
@@ -398,7 +401,7 @@ void run_single(Op& op, const int* pPos) {
     const int nwc = (op.kind == OP_ATTN) ? std::max(default_nwc(), 8) : default_nwc();
     if (!make_plan(pl, nwc, xs, meta, 0)) unsupported();      // a single op only ever uses buffer 0
     if (op.kind <= OP_CLS && !op_set_chunking(op, pl.ring_bytes)) unsupported();
-    launch_interp(pl, nullptr, 1, &op, pPos, -1, false, grid);
+    launch_interp(pl, nullptr, 1, &op, pPos, -1, false, grid, nullptr, op.kind == OP_ATTN);      // the position is on the device: the attention op always gets the instance that can split
 }
 
 // ------------------------------------------------------------------------------- temperature / top-p sampler (scope row f3)
@@ -871,7 +874,9 @@ static NetPlan& get_net_plan(Config* p, RunState* s, TransformerWeights* w) {
         if (op.kind <= OP_CLS && !op_set_chunking(op, np.plan.ring_bytes)) return np;
     // the persistent kernel needs one co-resident CTA per SM
     int per_sm = 0;
-    LQ4_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, interp_kernel, 32 * (nwc + 1), np.plan.smem));
+    LQ4_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, interp_kernel<true>, 32 * (nwc + 1), np.plan.smem));
+    if (per_sm < 1) return np;
+    LQ4_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, interp_kernel<false>, 32 * (nwc + 1), np.plan.smem));
     if (per_sm < 1) return np;
     np.nops = (int)ops.size();
     LQ4_CHECK(cudaMalloc((void**)&np.d_ops, sizeof(Op) * ops.size()));
@@ -881,14 +886,14 @@ static NetPlan& get_net_plan(Config* p, RunState* s, TransformerWeights* w) {
 }
 
 // one persistent launch: the forward pass, and the greedy sampler too when with_argmax
-static bool run_network_fused(int* pPos, Config* p, RunState* s, TransformerWeights* w, bool with_argmax, int write_token) {
+static bool run_network_fused(int* pPos, Config* p, RunState* s, TransformerWeights* w, bool with_argmax, int write_token, int seq_len) {
     NetPlan& np = get_net_plan(p, s, w);
     if (!np.ok) return false;
     if (pPos != s->pos) {
         fprintf(stderr, "lq4: run_llama_network expects pPos == RunState::pos\n");
         exit(EXIT_FAILURE);
     }
-    launch_interp(np.plan, np.d_ops, with_argmax ? np.nops : np.nops - 1, nullptr, pPos, write_token, true, g.sm_count, &np);
+    launch_interp(np.plan, np.d_ops, with_argmax ? np.nops : np.nops - 1, nullptr, pPos, write_token, true, g.sm_count, &np, seq_len > kAttnSplitFrom);
     return true;
 }
 
@@ -905,7 +910,7 @@ static bool run_network_fused(int* pPos, Config* p, RunState* s, TransformerWeig
 void lq4_run_llama_network(int* pPos, Config* p, RunState* s, TransformerWeights* w, int seq_len_bin) {
     ensure_init();
     if (g.tp_world > 1) tp_unsupported("run_llama_network without the fused sampler");
-    if (g.opt_fused && run_network_fused(pPos, p, s, w, false, -1)) return;
+    if (g.opt_fused && run_network_fused(pPos, p, s, w, false, -1, seq_len_bin)) return;      // the bin bounds the position from above
     run_network_unfused(pPos, p, s, w, seq_len_bin);
 }
 
@@ -987,7 +992,7 @@ static void forward_and_sample(int gen_token, Config* p, RunState* s, Transforme
                                Sampler* pSampler, int seq_len) {
     const int seq_len_bin = seq_len_bin_of(p, seq_len);
     if (g.opt_fused && !copyLogits && is_greedy(pSampler, gen_token)) {
-        if (run_network_fused(s->pos, p, s, w, true, gen_token != 0)) {      // greedy sampler = last op of the persistent kernel
+        if (run_network_fused(s->pos, p, s, w, true, gen_token != 0, seq_len)) {      // greedy sampler = last op of the persistent kernel
             (void)random_u32(&pSampler->rng_state);
             return;
         }

@@ -393,9 +393,72 @@ struct Smem {            // shared-memory map (shared-window addresses)
 // run of whole columns -- adjacent columns are contiguous in the reference layout, so a slot is one or two
 // multi-KB bulk copies (the TMA unit sustains ~1 copy per 70 cycles per SM: copies must be large).
 // ------------------------------------------------------------------------------------------------
+// Lookahead of the producer: walks the same (op, task, slot) sequence as the issue loop, kPrefetchAhead slots further on, and
+// asks the L2 for each slot's bytes (cp.async.bulk.prefetch.L2).  A slot that could not be requested into shared memory yet --
+// the ring is full, or it is draining for a new slot size -- then arrives from the L2 instead of from HBM once its turn comes.
+// MEASURED AND LEFT OFF (default 0): with 24 or 48 slots of lookahead the 7B step went from 2.03 to 2.25 ms on the same build --
+// the extra L2 traffic of the prefetches competes with the bulk copies that are already in flight.
+#ifndef LQ4_PREFETCH_AHEAD
+#define LQ4_PREFETCH_AHEAD 0
+#endif
+constexpr int kPrefetchAhead = LQ4_PREFETCH_AHEAD;
+__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+struct ProdAhead {
+    int o, task, i, t1;                 // op, warp-task, slot of the task, end of this CTA's task range
+    int kind, cps, spt, rpt, nseg, nc0, nc1, rows_total, row_stride, K;
+    size_t colb;
+    const uint8_t* w[3];
+};
+__device__ __forceinline__ bool ahead_open_op(const InterpParams& P, const Op* ops, ProdAhead& f) {      // first op at or after f.o with work for this CTA
+    for (; f.o < P.nops; f.o++) {
+        const Op* op = ops + f.o;
+        if (op->kind > OP_CLS) continue;
+        int t0, t1;
+        cta_task_range(*op, blockIdx.x, gridDim.x, t0, t1);
+        if (t1 <= t0) continue;
+        f.task = t0; f.t1 = t1; f.i = 0;
+        f.kind = op->kind; f.cps = op->cps; f.spt = op->spt; f.rpt = op->rpt; f.nseg = op->nseg; f.K = op->K;
+        f.nc0 = op->seg[0].ncols; f.nc1 = op->seg[1].ncols; f.rows_total = op->seg[0].ncols; f.row_stride = op->row_stride;
+        f.colb = (op->kind == OP_CLS) ? (size_t)op->K * 2 : (size_t)q4_col_bytes(op->K);
+        f.w[0] = (const uint8_t*)op->seg[0].w; f.w[1] = (const uint8_t*)op->seg[1].w; f.w[2] = (const uint8_t*)op->seg[2].w;
+        return true;
+    }
+    return false;
+}
+__device__ __forceinline__ void ahead_step(const InterpParams& P, const Op* ops, ProdAhead& f) {
+    if (f.o >= P.nops) return;
+    const uint32_t bytes = (uint32_t)(f.cps * f.colb);
+    if (f.kind == OP_GEMV) {
+        int col = f.task * 4, seg = 0;
+        if (f.nseg > 1 && col >= f.nc0) { col -= f.nc0; seg = 1; if (f.nseg > 2 && col >= f.nc1) { col -= f.nc1; seg = 2; } }
+        prefetch_l2(f.w[seg] + (size_t)(col + f.i * f.cps) * f.colb, bytes);
+    } else if (f.kind == OP_FFN) {
+        const size_t off = (size_t)(f.task * 2 + f.i * f.cps) * f.colb;
+        prefetch_l2(f.w[0] + off, bytes);
+        prefetch_l2(f.w[1] + off, bytes);
+    } else if (f.row_stride == f.K) {
+        const int row = f.task * f.rpt + f.i * f.cps;
+        int rows = f.rows_total - row;
+        if (rows > f.cps) rows = f.cps;
+        if (rows > 0) prefetch_l2(f.w[0] + (size_t)row * f.colb, (uint32_t)(rows * f.colb));
+    }
+    if (++f.i == f.spt) {
+        f.i = 0;
+        if (++f.task == f.t1) { f.o++; ahead_open_op(P, ops, f); }
+    }
+}
+
 __device__ void producer_loop(const InterpParams& P, const Op* ops, const Smem& sm) {
     uint64_t policy;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    ProdAhead ahead;
+    if constexpr (kPrefetchAhead > 0) {
+        ahead.o = 0;
+        if (ahead_open_op(P, ops, ahead))
+            for (int n = 0; n < kPrefetchAhead; n++) ahead_step(P, ops, ahead);
+    }
     // Ring epochs: consecutive ops with the same slot size share one; when the size changes the producer first waits for
     // every slot to be released (the consumers are then inside their hand-over / staging, which hides the refill) and
     // starts again at slot 0 with the new geometry.  pfill[i] = fills of slot i so far (parity of its barriers).
@@ -480,6 +543,7 @@ __device__ void producer_loop(const InterpParams& P, const Op* ops, const Smem& 
                     }
                 }
                 asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(pfill + slot * 4), "r"(pf + 1) : "memory");
+                if constexpr (kPrefetchAhead > 0) ahead_step(P, ops, ahead);      // keep the L2 lookahead kPrefetchAhead slots in front
                 if (++slot == S) slot = 0;
                 issued++;
                 asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(sm.bars + 3584), "r"(issued) : "memory");
@@ -1140,9 +1204,13 @@ __device__ __forceinline__ void attn_tile_async(const Ctx& c, const half* base, 
 }
 __device__ __forceinline__ int attn_parts(const Op& op, int pos, int grid);
 __device__ __forceinline__ void attn_rows_async(const Ctx& c, uint32_t dst, const half* src, int stride_elems, int row_bytes, int nrows);
+// SPLIT: the kernel instance that carries the several-CTAs-per-head attention (interp_kernel<true>, launched by the host once the
+// position passes kAttnSplitFrom).  The short-context instance holds none of that code: merely compiling it in cost 8 % of the
+// 7B step (1.88 -> 2.03 ms; register allocation of the staging and task loops), so it lives in its own instantiation.
+template <bool SPLIT>
 __device__ void attn_prefetch(const Ctx& c, const Op& op) {
     const int hs = op.head_size;
-    const int S = attn_parts(op, c.pos, (int)gridDim.x);
+    const int S = SPLIT ? attn_parts(op, c.pos, (int)gridDim.x) : 1;
     if (S > 1) {                                    // split mode: my K tiles are part_id, part_id + S, ... of head blockIdx.x / S
         const int h = blockIdx.x / S, part_id = blockIdx.x - h * S;
         if (h >= op.n_heads) return;
@@ -1621,9 +1689,10 @@ __device__ void run_attn_split(Ctx& c, const Op& op, bool prefetched) {
     trace_mark(c, 7);
 }
 
+template <bool SPLIT>
 __device__ void run_attn(Ctx& c, const Op& op, bool prefetched) {
-    const int S = attn_parts(op, c.pos, (int)gridDim.x);
-    if (S > 1) {      // attn_parts admits S > 1 only when (hs / 32) % S == 0
+    const int S = SPLIT ? attn_parts(op, c.pos, (int)gridDim.x) : 1;
+    if (SPLIT && S > 1) {      // attn_parts admits S > 1 only when (hs / 32) % S == 0
         if (op.head_size == 128 && S == 4) run_attn_split<4, 4>(c, op, prefetched);
         else if (op.head_size == 128) run_attn_split<4, 2>(c, op, prefetched);
         else run_attn_split<2, 2>(c, op, prefetched);
@@ -1705,6 +1774,7 @@ __device__ void run_argmax(Ctx& c, const Op& op, int write_token) {
 // ------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------
+template <bool SPLIT>
 __global__ void __launch_bounds__(32 * (kMaxConsumerWarps + 1), 1) interp_kernel(const __grid_constant__ InterpParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1768,7 +1838,7 @@ __global__ void __launch_bounds__(32 * (kMaxConsumerWarps + 1), 1) interp_kernel
         c.tag_out = ((P.seq_base + (unsigned)o + 1u) & 0x7FFFu) | 0x8000u;     // never 0: a zeroed buffer is never "fresh"
         c.tag_in = ((P.seq_base + (unsigned)o) & 0x7FFFu) | 0x8000u;           // the previous op's
         const bool attn_pref = (ops[o].kind == OP_ATTN);
-        if (attn_pref) attn_prefetch(c, ops[o]);   // K rows of earlier positions do not depend on this launch at all
+        if (attn_pref) attn_prefetch<SPLIT>(c, ops[o]);   // K rows of earlier positions do not depend on this launch at all
         if (sync_before) {
             c.nsync++;
             if (c.ctid == 0) grid_wait(P.sync, c.nsync * gridDim.x);
@@ -1781,7 +1851,7 @@ __global__ void __launch_bounds__(32 * (kMaxConsumerWarps + 1), 1) interp_kernel
             case OP_GEMV:
             case OP_FFN: run_q4(c, op); break;
             case OP_CLS: run_cls(c, op); break;
-            case OP_ATTN: run_attn(c, op, attn_pref); break;
+            case OP_ATTN: run_attn<SPLIT>(c, op, attn_pref); break;
             case OP_ARGMAX: run_argmax(c, op, (P.write_token >= 0) ? P.write_token : op.write_token); break;
             default: break;
         }

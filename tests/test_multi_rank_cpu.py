@@ -55,3 +55,44 @@ def test_single_rank_aggregation_is_identity():
     import bench
     assert bench.max_over_ranks(1.5, 1) == 1.5
     assert bench.aggregate_throughput(256, 0.5, 1) == 512.0
+
+
+def test_ids_match_reduction_gloo_world2():
+    """bench.py's in-run parity flag of a tensor-parallel run is the MIN over ranks of "my TP ids equal my one-GPU ids":
+    one dissenting rank must turn it off for the whole job."""
+    code = textwrap.dedent(f"""
+        import os, sys, json
+        sys.path.insert(0, {ROOT!r})
+        import torch.distributed as dist
+        import bench
+        dist.init_process_group("gloo")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        all_ok = bench.min_over_ranks(1.0, world, device="cpu") == 1.0
+        one_bad = bench.min_over_ranks(0.0 if rank == 1 else 1.0, world, device="cpu") == 1.0
+        if rank == 0:
+            print("RESULT " + json.dumps({{"all_ok": all_ok, "one_bad": one_bad}}))
+        dist.barrier()
+        dist.destroy_process_group()
+    """)
+    r = _torchrun(code)
+    assert r.returncode == 0, r.stderr[-800:]
+    res = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][0][7:])
+    assert res == {"all_ok": True, "one_bad": False}
+
+
+def test_reference_arm_prints_once_and_never_loads_the_engine():
+    """`bench.py --impl reference` under torchrun: rank 0 alone prints ONE JSON line, the other ranks exit 0 silently.  Without a
+    CUDA device (this container) the line says `unavailable` -- the reference is a CUDA program -- and the process must not
+    have mapped libllama_q4_b200.so: the synthetic .bin comes from the stand-alone writer."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", PYTHONPATH=ROOT, LQ4_LIB="/nonexistent/libllama_q4_b200.so")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29519", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "4", "--warmup", "3",
+                        "--model", "tiny", "--no-cpu-baseline"], capture_output=True, text=True, timeout=240, env=env)
+    assert r.returncode == 0, r.stderr[-800:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference"
+    import torch
+    if not torch.cuda.is_available():
+        assert "unavailable" in d
