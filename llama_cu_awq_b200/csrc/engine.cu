@@ -93,6 +93,21 @@ struct Engine {
 };
 Engine g;
 
+// The persistent kernel's instances (interp_sm100.cuh, kSplit | kTP | kDev): production launches take the leanest instance that
+// covers them; anything with the development aids switched on takes the full one.
+typedef void (*InterpFn)(const InterpParams);
+constexpr int kNumInterpInstances = 5;
+InterpFn interp_instance(int i) {
+    switch (i) {
+        case 0: return interp_kernel<0>;
+        case 1: return interp_kernel<kSplit>;
+        case 2: return interp_kernel<kTP>;
+        case 3: return interp_kernel<kSplit | kTP>;
+        default: return interp_kernel<kSplit | kTP | kDev>;
+    }
+}
+InterpFn interp_pick(bool long_ctx, bool tp, bool dev) { return interp_instance(dev ? 4 : (long_ctx ? 1 : 0) + (tp ? 2 : 0)); }
+
 void set_err(const char* what, cudaError_t e) {
     snprintf(g.err, sizeof g.err, "%s: %s", what, cudaGetErrorString(e));
     fprintf(stderr, "lq4: %s\n", g.err);
@@ -134,8 +149,8 @@ void ensure_init() {
     if ((env = getenv("LQ4_SLOT_BYTES"))) g.opt_slot_bytes = atoi(env);
     LQ4_CHECK(cudaMalloc((void**)&g.sync, 2 * sizeof(unsigned)));
     LQ4_CHECK(cudaMemset(g.sync, 0, 2 * sizeof(unsigned)));
-    LQ4_CHECK(cudaFuncSetAttribute(interp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.max_smem));
-    LQ4_CHECK(cudaFuncSetAttribute(interp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.max_smem));
+    for (int f = 0; f < kNumInterpInstances; f++)
+        LQ4_CHECK(cudaFuncSetAttribute(interp_instance(f), cudaFuncAttributeMaxDynamicSharedMemorySize, g.max_smem));
     g.inited = true;
 }
 
@@ -366,7 +381,8 @@ void launch_interp(const Plan& pl, const Op* d_ops, int nops, const Op* one, con
         cfg.attrs = attr;
         cfg.numAttrs = 1;
     }
-    cudaError_t e = long_ctx ? cudaLaunchKernelEx(&cfg, interp_kernel<true>, P) : cudaLaunchKernelEx(&cfg, interp_kernel<false>, P);
+    const bool dev = (P.trace != nullptr) || P.nomath;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, interp_pick(long_ctx, tp != nullptr, dev), P);
     if (e != cudaSuccess) { set_err("interp_kernel launch", e); exit(EXIT_FAILURE); }
 }
 
@@ -874,10 +890,10 @@ static NetPlan& get_net_plan(Config* p, RunState* s, TransformerWeights* w) {
         if (op.kind <= OP_CLS && !op_set_chunking(op, np.plan.ring_bytes)) return np;
     // the persistent kernel needs one co-resident CTA per SM
     int per_sm = 0;
-    LQ4_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, interp_kernel<true>, 32 * (nwc + 1), np.plan.smem));
-    if (per_sm < 1) return np;
-    LQ4_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, interp_kernel<false>, 32 * (nwc + 1), np.plan.smem));
-    if (per_sm < 1) return np;
+    for (int f = 0; f < kNumInterpInstances; f++) {
+        LQ4_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, interp_instance(f), 32 * (nwc + 1), np.plan.smem));
+        if (per_sm < 1) return np;
+    }
     np.nops = (int)ops.size();
     LQ4_CHECK(cudaMalloc((void**)&np.d_ops, sizeof(Op) * ops.size()));
     LQ4_CHECK(cudaMemcpy(np.d_ops, ops.data(), sizeof(Op) * ops.size(), cudaMemcpyHostToDevice));

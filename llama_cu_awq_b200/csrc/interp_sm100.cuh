@@ -215,8 +215,9 @@ __device__ __forceinline__ void st_tagged_all(const InterpParams& P, uint32_t* p
     const size_t off = (size_t)(p - P.peers[P.rank]);
     for (int r = 0; r < P.world; r++) st_tagged(P.peers[r] + off, tag, hbits);
 }
+template <int F>
 __device__ __forceinline__ void st_tagged_maybe_all(const InterpParams& P, bool bcast, uint32_t* p, uint32_t tag, uint32_t hbits) {
-    if (bcast && P.world > 1) st_tagged_all(P, p, tag, hbits);
+    if ((F & 2) && bcast && P.world > 1) st_tagged_all(P, p, tag, hbits);
     else st_tagged(p, tag, hbits);
 }
 // Two adjacent elements in one 8-byte store (every word carries its own tag, so readers need no atomicity across words;
@@ -224,8 +225,9 @@ __device__ __forceinline__ void st_tagged_maybe_all(const InterpParams& P, bool 
 __device__ __forceinline__ void st_tagged2(uint32_t* p, uint32_t tag, uint32_t h0, uint32_t h1) {
     asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"((tag << 16) | (h0 & 0xFFFFu)), "r"((tag << 16) | (h1 & 0xFFFFu)) : "memory");
 }
+template <int F>
 __device__ __forceinline__ void st_tagged2_maybe_all(const InterpParams& P, bool bcast, uint32_t* p, uint32_t tag, uint32_t h0, uint32_t h1) {
-    if (bcast && P.world > 1) {
+    if ((F & 2) && bcast && P.world > 1) {
         const size_t off = (size_t)(p - P.peers[P.rank]);
         for (int r = 0; r < P.world; r++) st_tagged2(P.peers[r] + off, tag, h0, h1);
     } else {
@@ -574,11 +576,24 @@ struct Ctx {
     unsigned op_seq;          // launch counter * nops + op index + 1: unique per (launch, op) for 2^30 ops (split-attention flags)
     unsigned long long* tr;   // detailed phase trace of the current op (this CTA's 8 entries) or nullptr
 };
-__device__ __forceinline__ void cyc_mark(const Ctx& c, int k) {      // SM clock, warp 0 lane 0: sub-microsecond phases
+// Kernel instances.  The persistent kernel is compiled several times, each instance holding only the code its launches can
+// reach: merely carrying the long-context attention cost the 7B step 8 % (register allocation of the staging and task loops),
+// the tensor-parallel stores and the development aids (phase trace, LQ4_NOMATH) another 3 %.
+constexpr int kSplit = 1;      // several CTAs per head for long contexts (run_attn_split); launched once the position passes kAttnSplitFrom
+constexpr int kTP = 2;         // tagged outputs are broadcast to every rank's buffer (world > 1)
+constexpr int kDev = 4;        // phase trace and the no-arithmetic timing mode
+template <int F>
+struct CtxT : Ctx {};
+
+template <int F>
+__device__ __forceinline__ void cyc_mark(const CtxT<F>& c, int k) {      // SM clock, warp 0 lane 0: sub-microsecond phases
+    if constexpr (!(F & kDev)) return;
     if (c.tr != nullptr && c.lane == 0 && c.warp == 0) (c.tr - blockIdx.x * 8 + 148 * 8 + blockIdx.x * 16)[k] = (unsigned long long)clock64();
 }
 // development aid: a raw value (not a clock) in slot k (8..15) of the CTA's cycle record
-__device__ __forceinline__ void val_mark(const Ctx& c, int k, unsigned long long v) {
+template <int F>
+__device__ __forceinline__ void val_mark(const CtxT<F>& c, int k, unsigned long long v) {
+    if constexpr (!(F & kDev)) return;
     if (c.tr != nullptr && c.lane == 0 && c.warp == 0) (c.tr - blockIdx.x * 8 + 148 * 8 + blockIdx.x * 16)[k] = v;
 }
 __device__ __forceinline__ unsigned producer_issued(const Ctx& c) {
@@ -586,7 +601,9 @@ __device__ __forceinline__ unsigned producer_issued(const Ctx& c) {
     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(c.sm.bars + 3584) : "memory");
     return v;
 }
-__device__ __forceinline__ void trace_mark(const Ctx& c, int k) {
+template <int F>
+__device__ __forceinline__ void trace_mark(const CtxT<F>& c, int k) {
+    if constexpr (!(F & kDev)) return;
     if (c.tr != nullptr && c.lane == 0 && (c.warp == 0 || k >= 8)) c.tr[k & 7] = global_ns();
 }
 
@@ -700,8 +717,8 @@ __device__ __forceinline__ void norm_take(const Op& op, const SlotMap& m, uint32
     }
 }
 
-template <bool PAIRS>
-__device__ __forceinline__ void stage_norm(Ctx& c, const Op& op, const half* xin) {
+template <bool PAIRS, int F>
+__device__ __forceinline__ void stage_norm(CtxT<F>& c, const Op& op, const half* xin) {
     const int K = op.K, T = (K + 1023) >> 10;
     const uint32_t red = c.sm.bars + kRedOffset;
     const bool worker = c.ctid < kNormThreads;
@@ -798,7 +815,8 @@ __device__ __forceinline__ void stage_norm(Ctx& c, const Op& op, const half* xin
 
 // Staging for the INT4 ops: x (fp16: tagged words, plain global, or an embedding row) -> fp32 pairs in shared memory.
 // The caller has already passed a named barrier: nobody reads the staging area any more.
-__device__ void stage_x_pairs(Ctx& c, const Op& op) {
+template <int F>
+__device__ void stage_x_pairs(CtxT<F>& c, const Op& op) {
     const int K = op.K;
     const half* xin = op.x;
     if (op.emb != nullptr) {
@@ -964,7 +982,8 @@ __device__ __forceinline__ void ring_epoch(Ctx& c, int slot_bytes, int nslots) {
     c.sm.slot_bytes = slot_bytes;
 }
 
-__device__ void run_q4(Ctx& c, const Op& op) {
+template <int F>
+__device__ void run_q4(CtxT<F>& c, const Op& op) {
     int t0, t1;
     cta_task_range(op, blockIdx.x, gridDim.x, t0, t1);
     // everything that does not depend on the activations first: the hand-over below is where this warp waits anyway
@@ -979,7 +998,7 @@ __device__ void run_q4(Ctx& c, const Op& op) {
     stage_x_pairs(c, op);
     trace_mark(c, 2);                                    // activations staged
     cyc_mark(c, 3);
-    if (c.tr != nullptr) {
+    if ((F & kDev) && c.tr != nullptr) {
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         val_mark(c, 8, producer_issued(c)); val_mark(c, 10, c.qtotal); val_mark(c, 11, smid);
@@ -1024,14 +1043,14 @@ __device__ void run_q4(Ctx& c, const Op& op) {
             if ((i1 >> csh) != (i0 >> csh)) ring_next(c, r);
             w1 = c.sm.slot(r.slot) + (i1 & (cps - 1)) * colb;
         }
-        if (task == t0) { trace_mark(c, 3); cyc_mark(c, 5); if (c.tr != nullptr) val_mark(c, 9, producer_issued(c)); }   // warp 0: first task's weights are in shared memory
+        if (task == t0) { trace_mark(c, 3); cyc_mark(c, 5); if ((F & kDev) && c.tr != nullptr) val_mark(c, 9, producer_issued(c)); }   // warp 0: first task's weights are in shared memory
         w0 += j * 32 + sw * 16;
         w1 += j * 32 + sw * 16;
         unsigned long long acc0 = 0ull, acc1 = 0ull;
         const int tlive = (K - j * 64 + 1023) >> 10;      // trips in which this thread's lanes hold data
 #pragma unroll 1
         for (int t = 0; t < T; t++) {
-            if (t < tlive && !c.P->nomath) {
+            if (t < tlive && !((F & kDev) && c.P->nomath)) {
                 const ColMeta m0 = col_meta(scol0, zcol0, t, j), m1 = col_meta(scol1, zcol1, t, j);
                 q4_trip2(acc0, acc1, c.sm.xs + t * kTripBytes + j * 16, w0 + t * 512, w1 + t * 512, m0, m1);
             }
@@ -1055,7 +1074,7 @@ __device__ void run_q4(Ctx& c, const Op& op) {
                 val = __fmul_rn(val, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-val))));
                 val = __fmul_rn(val, v1);
                 const uint32_t hb = f2h_bits(val);
-                if (op.seg[0].out32 != nullptr) st_tagged_maybe_all(*c.P, op.seg[0].bcast != 0, op.seg[0].out32 + col, c.tag_out, hb);
+                if (op.seg[0].out32 != nullptr) st_tagged_maybe_all<F>(*c.P, op.seg[0].bcast != 0, op.seg[0].out32 + col, c.tag_out, hb);
                 else op.seg[0].out[col] = __ushort_as_half((unsigned short)hb);
             } else {
                 const Seg& sg = op.seg[seg];
@@ -1076,7 +1095,7 @@ __device__ void run_q4(Ctx& c, const Op& op) {
                     s1 = s1 + h2f_bits(o1);
                 }
                 const uint32_t h0 = f2h_bits(s0), h1 = f2h_bits(s1);
-                if (sg.out32 != nullptr) st_tagged2_maybe_all(*c.P, sg.bcast != 0, sg.out32 + col, c.tag_out, h0, h1);   // col is even
+                if (sg.out32 != nullptr) st_tagged2_maybe_all<F>(*c.P, sg.bcast != 0, sg.out32 + col, c.tag_out, h0, h1);   // col is even
                 if (dst != nullptr) { dst[col] = __ushort_as_half((unsigned short)h0); dst[col + 1] = __ushort_as_half((unsigned short)h1); }
             }
         }
@@ -1092,7 +1111,8 @@ __device__ void run_q4(Ctx& c, const Op& op) {
 // fp16 classifier consumer (mat_vec_kernel, gpu_kernels.h:109-139).  Reference lane L chains
 // k = (trip*32 + L)*8 + el over trips of 256 k; one thread is one reference lane of four rows.
 // ------------------------------------------------------------------------------------------------
-__device__ void run_cls(Ctx& c, const Op& op) {
+template <int F>
+__device__ void run_cls(CtxT<F>& c, const Op& op) {
     const int n = op.K, T = op.T, lane = c.lane, cps = op.cps, spt = op.spt;
     // ---- stage x as fp16 (through the fused RMSNorm); the caller has passed a named barrier ----
     if (op.norm_w != nullptr) {
@@ -1127,7 +1147,7 @@ __device__ void run_cls(Ctx& c, const Op& op) {
         float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         for (int t = 0; t < T; t++) {
             const int jx = (t * 32 + lane) * 8;
-            if (jx < n && !c.P->nomath) {
+            if (jx < n && !((F & kDev) && c.P->nomath)) {
                 const uint4 xv = lds_v4(c.sm.xs + jx * 2);
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
@@ -1207,10 +1227,10 @@ __device__ __forceinline__ void attn_rows_async(const Ctx& c, uint32_t dst, cons
 // SPLIT: the kernel instance that carries the several-CTAs-per-head attention (interp_kernel<true>, launched by the host once the
 // position passes kAttnSplitFrom).  The short-context instance holds none of that code: merely compiling it in cost 8 % of the
 // 7B step (1.88 -> 2.03 ms; register allocation of the staging and task loops), so it lives in its own instantiation.
-template <bool SPLIT>
-__device__ void attn_prefetch(const Ctx& c, const Op& op) {
+template <int F>
+__device__ void attn_prefetch(const CtxT<F>& c, const Op& op) {
     const int hs = op.head_size;
-    const int S = SPLIT ? attn_parts(op, c.pos, (int)gridDim.x) : 1;
+    const int S = (F & kSplit) ? attn_parts(op, c.pos, (int)gridDim.x) : 1;
     if (S > 1) {                                    // split mode: my K tiles are part_id, part_id + S, ... of head blockIdx.x / S
         const int h = blockIdx.x / S, part_id = blockIdx.x - h * S;
         if (h >= op.n_heads) return;
@@ -1231,8 +1251,8 @@ __device__ void attn_prefetch(const Ctx& c, const Op& op) {
     for (int ti = 0; ti < kAttnAhead; ti++) attn_tile_async(c, kb, op.kv_stride, hs, op.max_seq, ti, c.pos);
 }
 
-template <int NSER>
-__device__ void run_attn_t(Ctx& c, const Op& op, bool prefetched) {
+template <int NSER, int F>
+__device__ void run_attn_t(CtxT<F>& c, const Op& op, bool prefetched) {
     constexpr int NS = NSER;                               // hs / 32
     const int hs = op.head_size, nt = c.nthreads, tid = c.ctid, lane = c.lane, warp = c.warp;
     float* qs = reinterpret_cast<float*>(c.scratch);       // hs
@@ -1421,7 +1441,7 @@ __device__ void run_attn_t(Ctx& c, const Op& op, bool prefetched) {
             for (int o = 1; o < 32; o <<= 1)
 #pragma unroll
                 for (int w = 0; w < 32; w += 2 * o) v[w] = v[w] + v[w + o];
-            if (op.attn_out32 != nullptr) st_tagged_maybe_all(*c.P, op.attn_bcast != 0, op.attn_out32 + (size_t)h * hs + i, c.tag_out, f2h_bits(v[0]));
+            if (op.attn_out32 != nullptr) st_tagged_maybe_all<F>(*c.P, op.attn_bcast != 0, op.attn_out32 + (size_t)h * hs + i, c.tag_out, f2h_bits(v[0]));
             else op.attn_out[(size_t)h * hs + i] = __float2half_rn(v[0]);
         }
         named_bar(kBarAll, nt);
@@ -1465,8 +1485,8 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     return v;
 }
 
-template <int NSER, int S>
-__device__ void run_attn_split(Ctx& c, const Op& op, bool prefetched) {
+template <int NSER, int S, int F>
+__device__ void run_attn_split(CtxT<F>& c, const Op& op, bool prefetched) {
     constexpr int NS = NSER;                               // hs / 32
     constexpr int NSP = NS / S;                            // output dimensions per lane in the PV phase
     const int hs = op.head_size, nt = c.nthreads, tid = c.ctid, lane = c.lane, warp = c.warp;
@@ -1682,15 +1702,16 @@ __device__ void run_attn_split(Ctx& c, const Op& op, bool prefetched) {
 #pragma unroll
             for (int w = 0; w < 32; w += 2 * o) v[w] = v[w] + v[w + o];
         const size_t e = (size_t)h * hs + part_id * dsub + i;
-        if (op.attn_out32 != nullptr) st_tagged_maybe_all(*c.P, op.attn_bcast != 0, op.attn_out32 + e, c.tag_out, f2h_bits(v[0]));
+        if (op.attn_out32 != nullptr) st_tagged_maybe_all<F>(*c.P, op.attn_bcast != 0, op.attn_out32 + e, c.tag_out, f2h_bits(v[0]));
         else op.attn_out[e] = __float2half_rn(v[0]);
     }
     named_bar(kBarAll, nt);
     trace_mark(c, 7);
 }
 
-template <bool SPLIT>
-__device__ void run_attn(Ctx& c, const Op& op, bool prefetched) {
+template <int F>
+__device__ void run_attn(CtxT<F>& c, const Op& op, bool prefetched) {
+    constexpr bool SPLIT = (F & kSplit) != 0;
     const int S = SPLIT ? attn_parts(op, c.pos, (int)gridDim.x) : 1;
     if (SPLIT && S > 1) {      // attn_parts admits S > 1 only when (hs / 32) % S == 0
         if (op.head_size == 128 && S == 4) run_attn_split<4, 4>(c, op, prefetched);
@@ -1708,7 +1729,8 @@ __device__ void run_attn(Ctx& c, const Op& op, bool prefetched) {
 // ------------------------------------------------------------------------------------------------
 // Greedy sampler on CTA 0 (argmax_kernel, gpu_kernels.h:448-493).  Equal maxima: lowest index.
 // ------------------------------------------------------------------------------------------------
-__device__ void run_argmax(Ctx& c, const Op& op, int write_token) {
+template <int F>
+__device__ void run_argmax(CtxT<F>& c, const Op& op, int write_token) {
     if (blockIdx.x != 0) return;
     float* smax = c.red;
     int* sidx = reinterpret_cast<int*>(c.red + 32);
@@ -1750,7 +1772,7 @@ __device__ void run_argmax(Ctx& c, const Op& op, int write_token) {
     if (c.ctid == 0) {
         for (int w = 1; w < c.nwc; w++)
             if (smax[w] > max_val || (smax[w] == max_val && sidx[w] < max_pos)) { max_val = smax[w]; max_pos = sidx[w]; }
-        if (op.cand != nullptr && c.P->world > 1) {
+        if ((F & kTP) && op.cand != nullptr && c.P->world > 1) {
             // tensor parallel: every rank publishes the best of its vocabulary slice to all ranks, then picks the global
             // winner itself (largest value, lowest index on ties): all ranks write the same token without a host round trip
             const int rank = c.P->rank, world = c.P->world;
@@ -1774,7 +1796,7 @@ __device__ void run_argmax(Ctx& c, const Op& op, int write_token) {
 // ------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------
-template <bool SPLIT>
+template <int F>
 __global__ void __launch_bounds__(32 * (kMaxConsumerWarps + 1), 1) interp_kernel(const __grid_constant__ InterpParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1808,7 +1830,7 @@ __global__ void __launch_bounds__(32 * (kMaxConsumerWarps + 1), 1) interp_kernel
         return;
     }
 
-    Ctx c;
+    CtxT<F> c;
     c.P = &P; c.sm = sm;
     c.red = reinterpret_cast<float*>(smem + kRedOffset);
     c.scratch = smem + kCtrlBytes;
@@ -1826,7 +1848,7 @@ __global__ void __launch_bounds__(32 * (kMaxConsumerWarps + 1), 1) interp_kernel
         const int sync_before = ops[o].sync_before;
         if (ops[o].kind <= OP_CLS) ring_epoch(c, ops[o].slot_bytes, ops[o].nslots);
         trace_mark(c, 5);                          // previous op: every warp of this CTA is done
-        c.tr = (P.trace != nullptr && o == P.trace_op) ? P.trace + 2048 + blockIdx.x * 8 : nullptr;
+        c.tr = ((F & kDev) && P.trace != nullptr && o == P.trace_op) ? P.trace + 2048 + blockIdx.x * 8 : nullptr;
         trace_mark(c, 0);                          // this CTA arrives at the op
         cyc_mark(c, 7);
         if (c.ctid == 0) {
@@ -1838,25 +1860,25 @@ __global__ void __launch_bounds__(32 * (kMaxConsumerWarps + 1), 1) interp_kernel
         c.tag_out = ((P.seq_base + (unsigned)o + 1u) & 0x7FFFu) | 0x8000u;     // never 0: a zeroed buffer is never "fresh"
         c.tag_in = ((P.seq_base + (unsigned)o) & 0x7FFFu) | 0x8000u;           // the previous op's
         const bool attn_pref = (ops[o].kind == OP_ATTN);
-        if (attn_pref) attn_prefetch<SPLIT>(c, ops[o]);   // K rows of earlier positions do not depend on this launch at all
+        if (attn_pref) attn_prefetch(c, ops[o]);   // K rows of earlier positions do not depend on this launch at all
         if (sync_before) {
             c.nsync++;
             if (c.ctid == 0) grid_wait(P.sync, c.nsync * gridDim.x);
         }
         named_bar(kBarAll, c.nthreads);
-        if (P.trace != nullptr && blockIdx.x == 0 && c.ctid == 0) P.trace[o] = global_ns();
+        if ((F & kDev) && P.trace != nullptr && blockIdx.x == 0 && c.ctid == 0) P.trace[o] = global_ns();
         trace_mark(c, 1);                          // grid barrier passed
         cyc_mark(c, 0);
         switch (op.kind) {
             case OP_GEMV:
             case OP_FFN: run_q4(c, op); break;
             case OP_CLS: run_cls(c, op); break;
-            case OP_ATTN: run_attn<SPLIT>(c, op, attn_pref); break;
+            case OP_ATTN: run_attn(c, op, attn_pref); break;
             case OP_ARGMAX: run_argmax(c, op, (P.write_token >= 0) ? P.write_token : op.write_token); break;
             default: break;
         }
     }
-    if (P.trace != nullptr && blockIdx.x == 0 && c.ctid == 0) P.trace[P.nops] = global_ns();
+    if ((F & kDev) && P.trace != nullptr && blockIdx.x == 0 && c.ctid == 0) P.trace[P.nops] = global_ns();
     // leave the barrier counters at zero for the next launch: the last CTA out resets them
     if (c.nsync > 0) {
         named_bar(kBarAll, c.nthreads);

@@ -168,6 +168,32 @@ def require_ref_bin():
     return REF_BIN
 
 
+def our_ids_are_reference_argmaxes(path, ids_path, vocab):
+    """Teacher-force our id sequence through oracle/_ref/libq4ref.so; assert each generated id attains the maximum of the
+    reference's fp16 logits of the step before it; return how many of those maxima were tied."""
+    vals = [int(x) for x in open(ids_path).read().split()]
+    n_prompt, ids = vals[0], vals[1:]
+    r = ref()
+    assert r.ref_open(path.encode()) == 0
+    try:
+        toks = np.array(ids, dtype=np.int32)
+        r.ref_reset(toks.ctypes.data_as(C.c_void_p), len(toks))
+        lg = np.zeros(vocab, np.uint16)
+        nxt = C.c_int(0)
+        tied = 0
+        for step in range(len(ids) - 1):
+            r.ref_step(0, lg.ctypes.data_as(C.c_void_p), C.byref(nxt))
+            if step < n_prompt - 1:
+                continue                               # prompt positions: the next id is given, not sampled
+            f = lg.view(np.float16).astype(np.float32)
+            assert f[ids[step + 1]] == f.max(), f"our id {ids[step + 1]} at position {step + 1} is not an argmax of the reference's logits"
+            tied += int((f == f.max()).sum() > 1)
+        return tied
+    finally:
+        r.ref_close()
+
+
+
 # ------------------------------------------------------------------ torch device helpers (GPU only)
 def to_dev(a: np.ndarray):
     import torch

@@ -22,32 +22,6 @@ def _transcript(out):
     return out[out.index("Done!"): m.start()], int(m.group(2)), float(m.group(1))
 
 
-def _our_ids_are_reference_argmaxes(path, ids_path, vocab):
-    """Teacher-force our id sequence through oracle/_ref/libq4ref.so; assert each generated id attains the maximum of the
-    reference's fp16 logits of the step before it; return how many of those maxima were tied."""
-    import numpy as np
-    vals = [int(x) for x in open(ids_path).read().split()]
-    n_prompt, ids = vals[0], vals[1:]
-    r = H.ref()
-    assert r.ref_open(path.encode()) == 0
-    try:
-        toks = np.array(ids, dtype=np.int32)
-        r.ref_reset(toks.ctypes.data_as(C.c_void_p), len(toks))
-        lg = np.zeros(vocab, np.uint16)
-        nxt = C.c_int(0)
-        tied = 0
-        for step in range(len(ids) - 1):
-            r.ref_step(0, lg.ctypes.data_as(C.c_void_p), C.byref(nxt))
-            if step < n_prompt - 1:
-                continue                               # prompt positions: the next id is given, not sampled
-            f = lg.view(np.float16).astype(np.float32)
-            assert f[ids[step + 1]] == f.max(), f"our id {ids[step + 1]} at position {step + 1} is not an argmax of the reference's logits"
-            tied += int((f == f.max()).sum() > 1)
-        return tied
-    finally:
-        r.ref_close()
-
-
 @pytest.mark.parametrize("model", ["7b", "13b"])
 def test_full_size_transcript_equals_reference(model):
     sys.path.insert(0, H.ROOT)
@@ -75,7 +49,7 @@ def test_full_size_transcript_equals_reference(model):
         # The reference breaks argmax ties by a write race (gpu_kernels.h:474-479), so the two programs may legitimately part
         # ways -- but ONLY at a tied maximum.  Proof: replay OUR ids through the unmodified reference teacher-forced and
         # require every id we generated to be a maximal element of the REFERENCE's logits at that step.
-        ties = _our_ids_are_reference_argmaxes(path, ids_path, cfg["vocab_size"])
+        ties = H.our_ids_are_reference_argmaxes(path, ids_path, cfg["vocab_size"])
         assert ties > 0, f"{model}: transcripts differ after {common} pieces although no step of our run sat on a tied maximum"
         pytest.xfail(f"diverged after {common} pieces at a tied maximum of the reference's logits ({ties} tied step(s)): its tie-break is a write race")
 
