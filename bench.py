@@ -457,6 +457,7 @@ def main():
     n, secs1, out1 = eng.e2e(K, barrier)
     assert out1[1:n] == ids1[1:n], "pipelined host API and raw enqueue disagree on token ids"
     secs1 = max_over_ranks(secs1, world)
+    clk_single = clocks.stop() if not tp else None      # N = 1 / replicas: the sampler covers the two timed regions only, not the side records below
     extras = {}
     if world == 1 and not args.no_extras:
         # the op-by-op path (option fused = 0): the reference's op sequence through the per-op wrappers, ~10 launches per layer
@@ -513,7 +514,7 @@ def main():
                                   "how": "N independent streams, one per GPU, no data-path collective (aggregate over the slowest rank's time)"}})
         if not same and rank == 0:
             print("bench.py: tensor-parallel ids differ from the single-GPU ids", file=sys.stderr)
-    line["clocks"] = clocks.stop()
+    line["clocks"] = clk_single if clk_single is not None else clocks.stop()
     line.update(extras)
 
     if rank == 0 and world == 1 and not args.no_extras and args.model == "7b":

@@ -96,17 +96,20 @@ Engine g;
 // The persistent kernel's instances (interp_sm100.cuh, kSplit | kTP | kDev): production launches take the leanest instance that
 // covers them; anything with the development aids switched on takes the full one.
 typedef void (*InterpFn)(const InterpParams);
-constexpr int kNumInterpInstances = 5;
-InterpFn interp_instance(int i) {
-    switch (i) {
+constexpr int kNumInterpInstances = 8;
+InterpFn interp_instance(int f) {      // f = kSplit | kTP | kDev
+    switch (f) {
         case 0: return interp_kernel<0>;
-        case 1: return interp_kernel<kSplit>;
-        case 2: return interp_kernel<kTP>;
-        case 3: return interp_kernel<kSplit | kTP>;
-        default: return interp_kernel<kSplit | kTP | kDev>;
+        case 1: return interp_kernel<1>;
+        case 2: return interp_kernel<2>;
+        case 3: return interp_kernel<3>;
+        case 4: return interp_kernel<4>;
+        case 5: return interp_kernel<5>;
+        case 6: return interp_kernel<6>;
+        default: return interp_kernel<7>;
     }
 }
-InterpFn interp_pick(bool long_ctx, bool tp, bool dev) { return interp_instance(dev ? 4 : (long_ctx ? 1 : 0) + (tp ? 2 : 0)); }
+InterpFn interp_pick(bool long_ctx, bool tp, bool dev) { return interp_instance((long_ctx ? kSplit : 0) | (tp ? kTP : 0) | (dev ? kDev : 0)); }
 
 void set_err(const char* what, cudaError_t e) {
     snprintf(g.err, sizeof g.err, "%s: %s", what, cudaGetErrorString(e));
