@@ -774,13 +774,13 @@ static NetPlan& get_net_plan(Config* p, RunState* s, TransformerWeights* w) {
     np.world = T; np.rank = R;
     np.tokens = s->shared_data->tokens;
     if (T > 1 && (p->n_heads % T || p->n_kv_heads % T || (dim / T) % 8 || (hidden / T) % 8 || (kv_dim / T) % 8 || (p->vocab_size / T) % 8 ||
-                  p->vocab_size % T || p->vocab_size > 65535 || T > 8)) return np;
+                  p->vocab_size % T || T > 8)) return np;
     const int sdim = dim / T, shid = hidden / T, skv = kv_dim / T, sheads = p->n_heads / T, svoc = p->vocab_size / T;
     const int bc = (T > 1) ? 1 : 0;
     // activations of the fused step travel as tagged 32-bit words (interp_sm100.cuh, "flag-in-data"): no grid barrier
     // between the op that writes a vector and the op that reads it; under tensor parallelism the writer stores into every
     // rank's copy and each rank polls its own
-    const size_t ntag = (size_t)3 * dim + hidden + 2 * kv_dim + 16;
+    const size_t ntag = (size_t)3 * dim + hidden + 2 * kv_dim + 32;      // ... + 3 candidate words per rank
     LQ4_CHECK(cudaMalloc((void**)&np.tagged, ntag * sizeof(uint32_t)));
     LQ4_CHECK(cudaMemset(np.tagged, 0, ntag * sizeof(uint32_t)));
     for (int r = 0; r < 8; r++) np.peers[r] = nullptr;

@@ -115,7 +115,7 @@ struct Op {
     volatile int* pos_host;    // SharedData::pos
     int* pos_dev;              // RunState::pos
     int write_token;
-    uint32_t* cand;        // tensor parallel: [world][2] tagged (value, index) candidates of the ranks' vocabulary slices, or nullptr
+    uint32_t* cand;        // tensor parallel: [world][3] tagged (value, index low, index high) candidates of the ranks' vocabulary slices, or nullptr
     int vocab0;            // first vocabulary row of this rank's slice
 };
 
@@ -1776,12 +1776,14 @@ __device__ void run_argmax(CtxT<F>& c, const Op& op, int write_token) {
             // tensor parallel: every rank publishes the best of its vocabulary slice to all ranks, then picks the global
             // winner itself (largest value, lowest index on ties): all ranks write the same token without a host round trip
             const int rank = c.P->rank, world = c.P->world;
-            st_tagged_all(*c.P, op.cand + 2 * rank, c.tag_out, f2h_bits(max_val));
-            st_tagged_all(*c.P, op.cand + 2 * rank + 1, c.tag_out, (uint32_t)(max_pos + op.vocab0));
+            const uint32_t gidx = (uint32_t)(max_pos + op.vocab0);      // a tagged word carries 16 bits: the index travels as two of them
+            st_tagged_all(*c.P, op.cand + 3 * rank, c.tag_out, f2h_bits(max_val));
+            st_tagged_all(*c.P, op.cand + 3 * rank + 1, c.tag_out, gidx & 0xFFFFu);
+            st_tagged_all(*c.P, op.cand + 3 * rank + 2, c.tag_out, gidx >> 16);
             max_val = -INFINITY; max_pos = 0x7fffffff;
             for (int r = 0; r < world; r++) {
-                const float v = h2f_bits(poll1(op.cand + 2 * r, c.tag_out));
-                const int idx = (int)poll1(op.cand + 2 * r + 1, c.tag_out);
+                const float v = h2f_bits(poll1(op.cand + 3 * r, c.tag_out));
+                const int idx = (int)(poll1(op.cand + 3 * r + 1, c.tag_out) | (poll1(op.cand + 3 * r + 2, c.tag_out) << 16));
                 if (v > max_val || (v == max_val && idx < max_pos)) { max_val = v; max_pos = idx; }
             }
         }

@@ -239,9 +239,11 @@ def test_rope_rotation(eng, nh, nkv, hs, theta):
             assert (H.dev_u16(rq) == gq).all() and (H.dev_u16(rk) == gk).all(), f"pos {pos}"
 
 
-@pytest.mark.parametrize("nh,hs,kv_mul", [(4, 64, 1), (32, 128, 1), (8, 32, 4)])
-@pytest.mark.parametrize("pos", [0, 1, 31, 32, 33, 255, 700])
+@pytest.mark.parametrize("nh,hs,kv_mul", [(4, 64, 1), (32, 128, 1), (8, 32, 4), (40, 128, 1)])
+@pytest.mark.parametrize("pos", [0, 1, 31, 32, 33, 255, 383, 384, 700, 1000])
 def test_multi_head_attention(eng, nh, hs, kv_mul, pos):
+    """Positions from 384 on run several CTAs per head (interp_sm100.cuh, run_attn_split): 4 parts for (32, 128), 2 parts for
+    (4, 64) and -- 40 heads x 4 exceed the SM count -- for (40, 128), the 13B shape; (8, 32) stays on one CTA per head."""
     import torch
     E, lib = eng
     o = H.oracle()

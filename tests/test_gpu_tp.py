@@ -19,7 +19,7 @@ def _ngpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("cfg_name,world", [("TINY", 2), ("SMALL", 2), ("TINY_GQA", 2), ("7B", 2), ("SMALL", 4), ("7B", 4), ("SMALL", 8), ("7B", 8)])
+@pytest.mark.parametrize("cfg_name,world", [("TINY", 2), ("SMALL", 2), ("TINY_GQA", 2), ("TINY_BIGVOCAB", 2), ("7B", 2), ("SMALL", 4), ("7B", 4), ("SMALL", 8), ("7B", 8)])
 def test_tp_tokens_equal_single_gpu(cfg_name, world):
     if _ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
@@ -27,7 +27,8 @@ def test_tp_tokens_equal_single_gpu(cfg_name, world):
     lib = E.lib()
     assert lib.lq4_init(0) == 0
     full = cfg_name == "7B"                 # BASELINE.json configs[3]: the 7B model itself, sharded
-    cfg = E.LLAMA2_7B if full else getattr(H, cfg_name)
+    # TINY_BIGVOCAB: a vocabulary beyond 65535 (the sampler's cross-rank candidate index no longer fits one tagged word)
+    cfg = E.LLAMA2_7B if full else dict(H.TINY, vocab_size=70016) if cfg_name == "TINY_BIGVOCAB" else getattr(H, cfg_name)
     steps, prompt = 48, [1, 35, 72]
     with tempfile.TemporaryDirectory() as d:
         path, outp = os.path.join(d, "m.bin"), os.path.join(d, "tp.json")
