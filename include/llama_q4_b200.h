@@ -95,6 +95,8 @@ void* lq4_get_stream(void);               /* the cudaStream_t everything is enqu
 void lq4_set_stream(void* cuda_stream);   /* adopt a caller-owned stream (e.g. torch's) */
 int lq4_stream_synchronize(void);         /* cudaStreamSynchronize + cudaGetLastError; 0 on success */
 int lq4_stream_query(void);               /* non-blocking: 0 = everything enqueued has finished, 1 = still running, 2 = a CUDA error (see lq4_last_error) */
+/* last error text.  A device-side wait that gives up (5 s: a protocol bug, or a tensor-parallel peer that died) leaves a record
+ * in pinned host memory before it traps; the text then names what was waited for, the CTA, the SM and the rank. */
 const char* lq4_last_error(void);
 int lq4_sm_count(void);
 void lq4_set_option(const char* name, int value); /* "pdl" (0/1), "fused" (0/1), "graphs" (0/1) */

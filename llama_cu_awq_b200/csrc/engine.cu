@@ -89,6 +89,7 @@ struct Engine {
     unsigned* att_flags = nullptr;         // [heads][4], zero-initialised once
     int att_flag_heads = 0;
     unsigned op_seq = 0;                   // single-op launches: a fresh Ctx::op_seq base per launch
+    int* fault = nullptr;                  // [4] pinned host record a timed-out device wait leaves before it traps (interp_sm100.cuh, g_fault)
     char err[512] = {0};
 };
 Engine g;
@@ -112,7 +113,15 @@ InterpFn interp_instance(int f) {      // f = kSplit | kTP | kDev
 InterpFn interp_pick(bool long_ctx, bool tp, bool dev) { return interp_instance((long_ctx ? kSplit : 0) | (tp ? kTP : 0) | (dev ? kDev : 0)); }
 
 void set_err(const char* what, cudaError_t e) {
-    snprintf(g.err, sizeof g.err, "%s: %s", what, cudaGetErrorString(e));
+    int n = snprintf(g.err, sizeof g.err, "%s: %s", what, cudaGetErrorString(e));
+    if (g.fault != nullptr && g.fault[0] != 0 && n > 0 && n < (int)sizeof g.err) {      // the kernel said why it gave up
+        static const char* const what_timed_out[] = {"?", "weights (a bulk copy never completed)",
+            "activations (the previous op's output never arrived; under tensor parallelism: a dead or stalled peer)", "the grid barrier",
+            "a ring slot that was never released", "the split-attention score flags"};
+        const int code = g.fault[0];
+        snprintf(g.err + n, sizeof g.err - n, " -- device protocol time-out after 5 s waiting for %s on CTA %d (thread %d, SM %d, rank %d of %d)",
+                 what_timed_out[(code >= 1 && code <= 5) ? code : 0], g.fault[1], g.fault[2], g.fault[3], g.tp_rank, g.tp_world);
+    }
     fprintf(stderr, "lq4: %s\n", g.err);
 }
 
@@ -150,6 +159,9 @@ void ensure_init() {
     if ((env = getenv("LQ4_NOMATH"))) g.opt_nomath = atoi(env);
     if ((env = getenv("LQ4_NSLOTS"))) g.opt_nslots = atoi(env);
     if ((env = getenv("LQ4_SLOT_BYTES"))) g.opt_slot_bytes = atoi(env);
+    LQ4_CHECK(cudaMallocHost((void**)&g.fault, 4 * sizeof(int)));
+    memset(g.fault, 0, 4 * sizeof(int));
+    LQ4_CHECK(cudaMemcpyToSymbol(lq4::g_fault, &g.fault, sizeof(int*)));
     LQ4_CHECK(cudaMalloc((void**)&g.sync, 2 * sizeof(unsigned)));
     LQ4_CHECK(cudaMemset(g.sync, 0, 2 * sizeof(unsigned)));
     for (int f = 0; f < kNumInterpInstances; f++)

@@ -171,7 +171,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
                  : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     return done != 0;
 }
-// Bounded spin: a protocol bug must abort the launch (trap), never hang the device.
+// Bounded spin: a protocol bug -- or, under tensor parallelism, a peer that died -- must abort the launch, never hang the device.
+// Before the trap the thread leaves a record in pinned host memory (g_fault, set by the host at start-up), so that the host's
+// next stream query / synchronize can say WHAT timed out instead of a bare "unspecified launch failure":
+//   code 1 weights (a bulk copy never completed)   2 activations (the previous op's tagged output never arrived: on a
+//   tensor-parallel run, a dead or stalled peer)   3 grid barrier   4 ring slot never released   5 split-attention flags
+__device__ int* g_fault = nullptr;      // [4] pinned host: code, CTA, thread, rank-local SM id
+__device__ __noinline__ void protocol_timeout(int code) {
+    int* f = g_fault;
+    if (f != nullptr) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        f[1] = (int)blockIdx.x; f[2] = (int)threadIdx.x; f[3] = (int)smid;
+        __threadfence_system();
+        f[0] = code;
+        __threadfence_system();
+    }
+    asm volatile("trap;");
+}
+// Bounded spin, continued: every wait below gives up after kWaitLimitNs.
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -181,7 +199,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const unsigned long long t0 = global_ns();
     while (!mbar_try_wait(bar, parity))
-        if (global_ns() - t0 > kWaitLimitNs) asm volatile("trap;");
+        if (global_ns() - t0 > kWaitLimitNs) protocol_timeout(1);
+}
+// The producer's waits are for ring slots the consumers have yet to release.  When the consumers are themselves stuck (waiting
+// for activations that never come) the producer would time out too, and first: it gets twice the limit, so that the record the
+// host sees names the real cause.
+__device__ __forceinline__ void mbar_wait_release(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = global_ns();
+    while (!mbar_try_wait(bar, parity))
+        if (global_ns() - t0 > 2 * kWaitLimitNs) protocol_timeout(4);
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
@@ -246,7 +273,7 @@ __device__ __forceinline__ uint32_t poll1(const uint32_t* p, uint32_t tag) {   /
         const unsigned long long t0 = global_ns();
         do {
             asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-            if ((v >> 16) != tag && global_ns() - t0 > kWaitLimitNs) asm volatile("trap;");
+            if ((v >> 16) != tag && global_ns() - t0 > kWaitLimitNs) protocol_timeout(2);
         } while ((v >> 16) != tag);
     }
     return v & 0xFFFFu;
@@ -267,7 +294,7 @@ __device__ __forceinline__ uint4 poll8(const uint32_t* p, uint32_t tag) {
         do {
             __nanosleep(40);        // idle CTAs poll for a long time (e.g. the 116 without a head during attention): stay off the L2
             a = ld_vol_v4(p); b = ld_vol_v4(p + 4);
-            if (global_ns() - t0 > kWaitLimitNs) asm volatile("trap;");
+            if (global_ns() - t0 > kWaitLimitNs) protocol_timeout(2);
         } while (!(tags_ok(a, tag) && tags_ok(b, tag)));
     }
     return make_uint4((a.x & 0xFFFFu) | (a.y << 16), (a.z & 0xFFFFu) | (a.w << 16), (b.x & 0xFFFFu) | (b.y << 16), (b.z & 0xFFFFu) | (b.w << 16));
@@ -337,7 +364,7 @@ __device__ __forceinline__ void grid_wait(unsigned* counter, unsigned target) {
         const unsigned long long t0 = global_ns();
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-            if (v < target && global_ns() - t0 > kWaitLimitNs) asm volatile("trap;");
+            if (v < target && global_ns() - t0 > kWaitLimitNs) protocol_timeout(3);
         } while (v < target);
     }
 }
@@ -475,13 +502,13 @@ __device__ void producer_loop(const InterpParams& P, const Op* ops, const Smem& 
         cta_task_range(op, blockIdx.x, gridDim.x, t0, t1);
         const int cps = op.cps, spt = op.spt;
         if (op.slot_bytes != sbytes) {
-            for (int i = 0; i < S; i++) mbar_wait(sm.empty(i), (ld_fill(i) & 1) ^ 1);     // drain: last fill of every slot released
+            for (int i = 0; i < S; i++) mbar_wait_release(sm.empty(i), (ld_fill(i) & 1) ^ 1);     // drain: last fill of every slot released
             S = op.nslots; sbytes = op.slot_bytes; slot = 0;
         }
 
         if (op.kind != OP_CLS) {      // scales and zero points of the CTA's columns (layout: see stage_meta_layout)
             const int b = mcount & 1;
-            mbar_wait(sm.mempty(b), ((mcount >> 1) & 1) ^ 1);
+            mbar_wait_release(sm.mempty(b), ((mcount >> 1) & 1) ^ 1);
             const uint32_t dst = sm.mbuf(b), bar = sm.mfull(b);
             const int G = q4_groups(op.K), zh = q4_zh(op.K);
             if (t1 > t0) {
@@ -519,7 +546,7 @@ __device__ void producer_loop(const InterpParams& P, const Op* ops, const Smem& 
             if (op.kind == OP_GEMV) gemv_locate(op, task * 4, seg, col);
             for (int i = 0; i < spt; i++) {
                 const unsigned pf = ld_fill(slot);
-                mbar_wait(sm.empty(slot), (pf & 1) ^ 1);
+                mbar_wait_release(sm.empty(slot), (pf & 1) ^ 1);
                 const uint32_t dst = sm.ring + (uint32_t)slot * sbytes, bar = sm.full(slot);
                 if (op.kind == OP_GEMV) {
                     const uint32_t bytes = (uint32_t)(cps * colb);
@@ -689,7 +716,7 @@ __device__ __forceinline__ void poll_vecs(uint2 (&v)[N], Addr addr, uint32_t wan
 #pragma unroll
             for (int i = 0; i < N; i++)
                 if (((pend >> i) & 1u) && tags_ok2(v[i], tag)) pend &= ~(1u << i);
-            if (global_ns() - t0 > kWaitLimitNs) asm volatile("trap;");
+            if (global_ns() - t0 > kWaitLimitNs) protocol_timeout(2);
         } while (pend);
     }
 }
@@ -955,7 +982,7 @@ __device__ __forceinline__ void ring_wait(const Ctx& c, const RingPos& r) {
         const unsigned long long t0 = global_ns();
         do {
             asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(done) : "r"(c.sm.laps + r.slot * 4) : "memory");
-            if (global_ns() - t0 > kWaitLimitNs) asm volatile("trap;");
+            if (global_ns() - t0 > kWaitLimitNs) protocol_timeout(4);
         } while (done < need);
     }
     mbar_wait(c.sm.full(r.slot), need & 1);
@@ -1285,7 +1312,7 @@ __device__ void run_attn_t(CtxT<F>& c, const Op& op, bool prefetched) {
                     for (;;) {               // the four words are fetched together: one round trip per attempt, not four
                         q0b = ld_tagged_any(pq); q1b = ld_tagged_any(pq + hs / 2); k0b = ld_tagged_any(pk); k1b = ld_tagged_any(pk + hs / 2);
                         if (((q0b >> 16) == tag) & ((q1b >> 16) == tag) & ((k0b >> 16) == tag) & ((k1b >> 16) == tag)) break;
-                        if (global_ns() - t0 > kWaitLimitNs) asm volatile("trap;");
+                        if (global_ns() - t0 > kWaitLimitNs) protocol_timeout(2);
                     }
                     q0b &= 0xFFFFu; q1b &= 0xFFFFu; k0b &= 0xFFFFu; k1b &= 0xFFFFu;
                 } else {
@@ -1529,7 +1556,7 @@ __device__ void run_attn_split(CtxT<F>& c, const Op& op, bool prefetched) {
                 for (;;) {
                     q0b = ld_tagged_any(pq); q1b = ld_tagged_any(pq + hs / 2); k0b = ld_tagged_any(pk); k1b = ld_tagged_any(pk + hs / 2);
                     if (((q0b >> 16) == tag) & ((q1b >> 16) == tag) & ((k0b >> 16) == tag) & ((k1b >> 16) == tag)) break;
-                    if (global_ns() - t0 > kWaitLimitNs) asm volatile("trap;");
+                    if (global_ns() - t0 > kWaitLimitNs) protocol_timeout(2);
                 }
                 q0b &= 0xFFFFu; q1b &= 0xFFFFu; k0b &= 0xFFFFu; k1b &= 0xFFFFu;
             } else {
@@ -1608,7 +1635,7 @@ __device__ void run_attn_split(CtxT<F>& c, const Op& op, bool prefetched) {
         if (ld_acquire_u32(f) != c.op_seq) {
             const unsigned long long t0 = global_ns();
             while (ld_acquire_u32(f) != c.op_seq)
-                if (global_ns() - t0 > kWaitLimitNs) asm volatile("trap;");
+                if (global_ns() - t0 > kWaitLimitNs) protocol_timeout(5);
         }
     }
     named_bar(kBarAll, nt);

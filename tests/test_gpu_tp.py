@@ -73,3 +73,22 @@ def test_tp_refuses_what_it_cannot_do():
         % (H.ROOT, os.path.join(H.ROOT, "tests")))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "not available under tensor parallelism" in r.stderr and "survived" not in r.stdout
+
+
+def test_tp_dead_peer_is_diagnosed():
+    """A tensor-parallel peer that never launches: the surviving rank's kernel gives up after its 5 s limit, leaves a record in
+    pinned host memory before it traps, and the host reports WHAT timed out (the bare trap was undiagnosable)."""
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    import llama_cu_awq_b200 as E
+    lib = E.lib()
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "m.bin")
+        c = E.Config(**H.TINY)
+        assert lib.lq4_write_synth_model(path.encode(), C.byref(c), 3) == os.path.getsize(path)
+        env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                            "--master-port", "29537", os.path.join(H.ROOT, "tests", "tp_fault_worker.py"), path], capture_output=True, text=True,
+                           timeout=240, env=env)
+        assert "survived" not in r.stdout
+        assert "device protocol time-out" in r.stderr and "activations" in r.stderr, r.stderr[-1500:]
