@@ -266,7 +266,11 @@ def test_multi_head_attention(eng, nh, hs, kv_mul, pos):
                                  kv_mul, seq, dp.data_ptr())
     sync(lib)
     got = H.dev_u16(dout)
-    assert H.ulp_diff_f16(got, want).max() <= 2          # softmax expf: libm vs libdevice
+    # vs the CPU oracle: host libm vs CUDA expf differ in the last bit of a probability, and an output that is a sum of ~pos
+    # terms of mixed sign can sit near zero, where an fp16 ulp is tiny: 2 ulps, or 2^-9 of the largest output.  The bit-exact
+    # comparison is the one against the reference kernels below.
+    gf, wf = got.view(np.float16).astype(np.float32), want.view(np.float16).astype(np.float32)
+    assert ((H.ulp_diff_f16(got, want) <= 2) | (np.abs(gf - wf) <= 2.0 ** -9 * np.abs(wf).max())).all()
     if r is not None:
         ratt = H.to_dev(np.zeros(nh * seq, np.uint16))
         rout = H.to_dev(np.zeros(nh * hs, np.uint16))
