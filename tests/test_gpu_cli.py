@@ -182,3 +182,25 @@ def test_cli_chat_mode_matches_reference():
                 assert rr.returncode == 0
                 cut = lambda s: s[s.index("\nRendered prompt:"):]
                 assert cut(mine) == cut(rr.stdout)
+
+
+def test_cli_prefill_opt_in():
+    """LQ4_PREFILL=1: the prompt goes through the batched tensor-core prefill, decoding continues over the prefilled KV cache.
+    Same stdout shape (prompt echo, token count); the continuation agrees with the stepped run except possibly after a near-tie
+    (fp16 tolerance, not bit-exactness), so the check is a long common prefix, not equality."""
+    import llama_cu_awq_b200 as E
+    lib = E.lib()
+    cfg = H.SMALL
+    with tempfile.TemporaryDirectory() as d:
+        path, tok = os.path.join(d, "m.bin"), os.path.join(d, "tok.bin")
+        c = E.Config(**cfg)
+        assert lib.lq4_write_synth_model(path.encode(), C.byref(c), 99) == os.path.getsize(path)
+        assert lib.lq4_write_synth_tokenizer(tok.encode(), cfg["vocab_size"]) > 0
+        prompt = "the quick brown fox jumps over the lazy dog again and again"
+        args = [path, "-z", tok, "-t", "0", "-n", "96", "-i", prompt]
+        stepped, n0 = transcript(run(CLI, args))
+        prefilled, n1 = transcript(run(CLI, args, {"LQ4_PREFILL": "1"}))
+        assert n0 == n1 == 95
+        a, b = re.findall(r"\[\d+\]|.", stepped), re.findall(r"\[\d+\]|.", prefilled)
+        common = next((i for i, (x, y) in enumerate(zip(a, b)) if x != y), min(len(a), len(b)))
+        assert common >= len(prompt) + 4, f"the prefilled run leaves the stepped one after {common} pieces:\n{stepped[-200:]}\n{prefilled[-200:]}"
