@@ -99,7 +99,7 @@ int lq4_stream_query(void);               /* non-blocking: 0 = everything enqueu
  * in pinned host memory before it traps; the text then names what was waited for, the CTA, the SM and the rank. */
 const char* lq4_last_error(void);
 int lq4_sm_count(void);
-void lq4_set_option(const char* name, int value); /* "pdl" (0/1), "fused" (0/1), "graphs" (0/1) */
+void lq4_set_option(const char* name, int value); /* "pdl", "fused", "graphs", "opk" (0/1) ...: the run-time switches of INTEGRATION.md */
 
 /* development aid: per-op timestamps (ns) of the last fused step after lq4_set_option("trace", 1) */
 int lq4_debug_trace(unsigned long long* out, int* kinds, int max);

@@ -14,12 +14,16 @@ import helpers as H
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def eng():
+@pytest.fixture(scope="module", params=[0, 1], ids=["interp", "opk"])
+def eng(request):
+    """Every operator test runs twice: through one-op launches of the persistent kernel (the default) and, with option opk=1,
+    through the stand-alone kernels chained by programmatic dependent launch; both must give the reference's bits."""
     import llama_cu_awq_b200 as E
     lib = E.lib()
     assert lib.lq4_init(0) == 0
-    return E, lib
+    lib.lq4_set_option(b"opk", request.param)
+    yield E, lib
+    lib.lq4_set_option(b"opk", 0)
 
 
 def sync(lib):

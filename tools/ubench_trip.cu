@@ -101,12 +101,19 @@ __device__ __forceinline__ void q4_trip2_v4(unsigned long long& acc0, unsigned l
     }
 }
 
+// MAXW: warps per CTA (consumers + the producer lane's warp).  12 is the production kernel (168 registers per thread); -DMAXW=24
+// asks what a kernel that fitted 85 registers would gain from 23 consumer warps.
+#ifndef MAXW
+#define MAXW 12
+#endif
+static const int kActive[] = {1, 2, 4, 7, 8, 11, 12, 15, 16, 19, 20, 23};
+
 template <int VAR>
-__global__ void __launch_bounds__(384, 1) trip_kernel(const uint32_t* __restrict__ src, float* out, long long* cyc, int T, int ntasks, int active) {
+__global__ void __launch_bounds__(32 * MAXW, 1) trip_kernel(const uint32_t* __restrict__ src, float* out, long long* cyc, int T, int ntasks, int active) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int colb = T * 512;
-    const int xs_bytes = T * kTripBytes, w_bytes = 11 * 4 * colb, meta_bytes = 11 * 4 * 64;
+    const int xs_bytes = T * kTripBytes, w_bytes = (MAXW - 1) * 4 * colb, meta_bytes = (MAXW - 1) * 4 * 64;
     uint32_t* s32 = reinterpret_cast<uint32_t*>(smem);
     for (int i = tid; i < (xs_bytes + w_bytes + meta_bytes) / 4; i += blockDim.x) {
         uint32_t v = src[(i * 7 + blockIdx.x) & 0xFFFFF];
@@ -139,31 +146,32 @@ __global__ void __launch_bounds__(384, 1) trip_kernel(const uint32_t* __restrict
         sink += halfwarp_total(acc0) + halfwarp_total(acc1);
     }
     const long long t1 = clock64();
-    if (lane == 0) cyc[blockIdx.x * 12 + warp] = t1 - t0;
+    if (lane == 0) cyc[blockIdx.x * MAXW + warp] = t1 - t0;
     out[blockIdx.x * blockDim.x + tid] = sink;
 }
 
 template <int VAR>
 void run(const char* name, const uint32_t* src, float* out, long long* cyc, int sms) {
     const int T = 4, ntasks = 64;
-    const size_t smem = (size_t)T * kTripBytes + 11 * 4 * T * 512 + 11 * 4 * 64;
+    const size_t smem = (size_t)T * kTripBytes + (MAXW - 1) * 4 * T * 512 + (MAXW - 1) * 4 * 64;
     cudaFuncSetAttribute(trip_kernel<VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncAttributes fa;
     cudaFuncGetAttributes(&fa, trip_kernel<VAR>);
-    for (int active : {1, 2, 4, 7, 8, 11}) {
-        cudaMemset(cyc, 0, sizeof(long long) * sms * 12);
-        trip_kernel<VAR><<<sms, 384, smem>>>(src, out, cyc, T, ntasks, active);
+    for (int active : kActive) {
+        if (active > MAXW - 1) continue;
+        cudaMemset(cyc, 0, sizeof(long long) * sms * MAXW);
+        trip_kernel<VAR><<<sms, 32 * MAXW, smem>>>(src, out, cyc, T, ntasks, active);
         cudaDeviceSynchronize();
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0);
-        trip_kernel<VAR><<<sms, 384, smem>>>(src, out, cyc, T, ntasks, active);
+        trip_kernel<VAR><<<sms, 32 * MAXW, smem>>>(src, out, cyc, T, ntasks, active);
         cudaEventRecord(e1);
         cudaDeviceSynchronize();
         float ms; cudaEventElapsedTime(&ms, e0, e1);
-        std::vector<long long> h(sms * 12);
-        cudaMemcpy(h.data(), cyc, sizeof(long long) * sms * 12, cudaMemcpyDeviceToHost);
+        std::vector<long long> h(sms * MAXW);
+        cudaMemcpy(h.data(), cyc, sizeof(long long) * sms * MAXW, cudaMemcpyDeviceToHost);
         double sum = 0, mx = 0; int n = 0;
-        for (int b = 0; b < sms; b++) for (int w = 0; w < active; w++) { double c = (double)h[b * 12 + w]; sum += c; if (c > mx) mx = c; n++; }
+        for (int b = 0; b < sms; b++) for (int w = 0; w < active; w++) { double c = (double)h[b * MAXW + w]; sum += c; if (c > mx) mx = c; n++; }
         const double per_trip = sum / n / (ntasks * T);
         printf("%-34s regs %3d  active warps %2d: %7.0f clk per warp-trip (slowest warp %7.0f), %5.1f weights/clk/SM  [%0.3f ms, err %d]\n", name, fa.numRegs, active, per_trip,
                mx / (ntasks * T), active * 4096.0 / (mx / (ntasks * T)), ms, (int)cudaGetLastError());
@@ -173,7 +181,7 @@ void run(const char* name, const uint32_t* src, float* out, long long* cyc, int 
 int main() {
     int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     uint32_t* src; float* out; long long* cyc;
-    cudaMalloc(&src, 4 << 20); cudaMalloc(&out, sizeof(float) * sms * 384); cudaMalloc(&cyc, sizeof(long long) * sms * 12);
+    cudaMalloc(&src, 4 << 20); cudaMalloc(&out, sizeof(float) * sms * 32 * MAXW); cudaMalloc(&cyc, sizeof(long long) * sms * MAXW);
     std::vector<uint32_t> h(1 << 20);
     uint64_t s = 88172645463325252ull;
     for (auto& v : h) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; v = (uint32_t)s; }
