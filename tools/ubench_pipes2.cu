@@ -7,6 +7,9 @@
 #include <cuda_runtime.h>
 
 #define FH(d, a, s) asm volatile("{ .reg .b16 l, h, sl, sh; mov.b32 {l, h}, %1; mov.b32 {sl, sh}, %2; fma.rn.f32.f16 %0, l, sl, %0; }" : "+f"(d) : "r"(a), "r"(s))
+#define FHH(d, a, s) asm volatile("{ .reg .b16 l, h, sl, sh; mov.b32 {l, h}, %1; mov.b32 {sl, sh}, %2; fma.rn.f32.f16 %0, h, sl, %0; }" : "+f"(d) : "r"(a), "r"(s))
+#define FHC(d, a, s, c) asm volatile("{ .reg .b16 l, h, sl, sh; mov.b32 {l, h}, %1; mov.b32 {sl, sh}, %2; fma.rn.f32.f16 %0, l, sl, %3; }" : "=f"(d) : "r"(a), "r"(s), "f"(c))
+#define FHHC(d, a, s, c) asm volatile("{ .reg .b16 l, h, sl, sh; mov.b32 {l, h}, %1; mov.b32 {sl, sh}, %2; fma.rn.f32.f16 %0, h, sl, %3; }" : "=f"(d) : "r"(a), "r"(s), "f"(c))
 #define F2(d, w, x) asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(w), "l"(x))
 #define FF(d, w, x) asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(d) : "f"(w), "f"(x))
 #define LO(d, a) asm volatile("lop3.b32 %0, %0, %1, 0x64006400, 0xEA;" : "+r"(d) : "r"(a))
@@ -38,6 +41,37 @@ __global__ void __launch_bounds__(512, 1) k(float* out, long long* cyc, int iter
             if (MODE == 8) { FH(f[i], a, s); FF(f[i], wf, xf); }
             if (MODE == 9) { F2(p[i], w, x); LO(u[i], a); }
             if (MODE == 10) { FF(f[i], wf, xf); LO(u[i], a); }
+            if (MODE == 12) { FHH(f[i], a, s); }
+            if (MODE == 13) { FH(f[i], a, s); FHH(f[i], s, a); }
+            if (MODE == 14) {      // the real dequant8 shape: 4 LOP3 + 1 SHF + 8 FHFMA (4 of them .H1) with fresh destinations, + 8 FADD to consume
+                uint32_t p04, p15, p26, p37, w8;
+                asm volatile("lop3.b32 %0, %1, 0x000F000F, 0x64006400, 0xEA;" : "=r"(p04) : "r"(u[i]));
+                asm volatile("lop3.b32 %0, %1, 0x00F000F0, 0x54005400, 0xEA;" : "=r"(p15) : "r"(u[i]));
+                asm volatile("shr.u32 %0, %1, 8;" : "=r"(w8) : "r"(u[i]));
+                asm volatile("lop3.b32 %0, %1, 0x000F000F, 0x64006400, 0xEA;" : "=r"(p26) : "r"(w8));
+                asm volatile("lop3.b32 %0, %1, 0x00F000F0, 0x54005400, 0xEA;" : "=r"(p37) : "r"(w8));
+                float d0, d1, d2, d3, d4, d5, d6, d7;
+                FHC(d0, p04, s, wf); FHC(d1, p15, s, xf); FHC(d2, p26, s, wf); FHC(d3, p37, s, xf);
+                FHHC(d4, p04, s, wf); FHHC(d5, p15, s, xf); FHHC(d6, p26, s, wf); FHHC(d7, p37, s, xf);
+                asm volatile("add.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(d0)); asm volatile("add.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(d1));
+                asm volatile("add.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(d2)); asm volatile("add.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(d3));
+                asm volatile("add.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(d4)); asm volatile("add.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(d5));
+                asm volatile("add.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(d6)); asm volatile("add.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(d7));
+                u[i] += 0x01234567u;
+            }
+            if (MODE == 15) {      // the same with the accumulate of the trip: 8 FFMA on one chain
+                uint32_t p04, p15, p26, p37, w8;
+                asm volatile("lop3.b32 %0, %1, 0x000F000F, 0x64006400, 0xEA;" : "=r"(p04) : "r"(u[i]));
+                asm volatile("lop3.b32 %0, %1, 0x00F000F0, 0x54005400, 0xEA;" : "=r"(p15) : "r"(u[i]));
+                asm volatile("shr.u32 %0, %1, 8;" : "=r"(w8) : "r"(u[i]));
+                asm volatile("lop3.b32 %0, %1, 0x000F000F, 0x64006400, 0xEA;" : "=r"(p26) : "r"(w8));
+                asm volatile("lop3.b32 %0, %1, 0x00F000F0, 0x54005400, 0xEA;" : "=r"(p37) : "r"(w8));
+                float d0, d1, d2, d3, d4, d5, d6, d7;
+                FHC(d0, p04, s, wf); FHC(d1, p15, s, xf); FHC(d2, p26, s, wf); FHC(d3, p37, s, xf);
+                FHHC(d4, p04, s, wf); FHHC(d5, p15, s, xf); FHHC(d6, p26, s, wf); FHHC(d7, p37, s, xf);
+                FF(f[i], d0, xf); FF(f[i], d1, wf); FF(f[i], d2, xf); FF(f[i], d3, wf); FF(f[i], d4, xf); FF(f[i], d5, wf); FF(f[i], d6, xf); FF(f[i], d7, wf);
+                u[i] += 0x01234567u;
+            }
             if (MODE == 11) { FH(f[i], a, s); FH(f[i], s, a); FH(f[i], a, a); FH(f[i], s, s); FF(f[i], wf, xf); FF(f[i], xf, wf); FF(f[i], wf, wf); FF(f[i], xf, xf); LO(u[i], a); LO(u[i], s); SH(u[i]); }   // FFMA instead of FFMA2
         }
     }
@@ -79,5 +113,9 @@ int main() {
     run<9>("FFMA2 + LOP3", 2, out, cyc, sms);
     run<10>("FFMA + LOP3", 2, out, cyc, sms);
     run<11>("4 FHFMA + 4 FFMA + 2 LOP3 + 1 SHF", 11, out, cyc, sms);
+    run<12>("FHFMA .H1", 1, out, cyc, sms);
+    run<13>("FHFMA + FHFMA .H1", 2, out, cyc, sms);
+    run<14>("dequant8 (4 LOP3, SHF, 8 FHFMA) + 8 FADD + IADD", 22, out, cyc, sms);
+    run<15>("dequant8 (4 LOP3, SHF, 8 FHFMA) + 8 FFMA + IADD", 22, out, cyc, sms);
     return 0;
 }

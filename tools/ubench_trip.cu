@@ -101,6 +101,29 @@ __device__ __forceinline__ void q4_trip2_v4(unsigned long long& acc0, unsigned l
     }
 }
 
+// ---- variant 5: another work split: a thread is ONE reference lane of FOUR columns (instead of two lanes of two columns), so a
+// loaded x is used by four columns (8 instead of 16 x loads per trip) and the accumulate is the scalar FFMA.  x rows are plain
+// fp32 in k order, one 128-byte row per lane padded to 144 bytes (conflict-free 16-byte loads). ----
+constexpr int kRowBytes5 = 144, kTripBytes5 = 32 * kRowBytes5;
+__device__ __forceinline__ void q4_trip4_v5(float (&acc)[4], uint32_t xaddr, const uint32_t (&w)[4], const ColMeta (&m)[4]) {
+    uint4 wv[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) wv[c] = lds_v4(w[c]);
+#pragma unroll
+    for (int qi = 0; qi < 4; qi++) {
+        const uint4 xa = lds_v4(xaddr + qi * 32), xb = lds_v4(xaddr + qi * 32 + 16);
+        const float x[8] = {__uint_as_float(xa.x), __uint_as_float(xa.y), __uint_as_float(xa.z), __uint_as_float(xa.w),
+                            __uint_as_float(xb.x), __uint_as_float(xb.y), __uint_as_float(xb.z), __uint_as_float(xb.w)};
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            float d[8];
+            dequant8(d, word_of(wv[c], qi), m[c].s16, m[c].nlo, m[c].nhi);
+#pragma unroll
+            for (int e = 0; e < 8; e++) acc[c] = __fmaf_rn(d[e], x[e], acc[c]);
+        }
+    }
+}
+
 // MAXW: warps per CTA (consumers + the producer lane's warp).  12 is the production kernel (168 registers per thread); -DMAXW=24
 // asks what a kernel that fitted 85 registers would gain from 23 consumer warps.
 #ifndef MAXW
@@ -113,7 +136,7 @@ __global__ void __launch_bounds__(32 * MAXW, 1) trip_kernel(const uint32_t* __re
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int colb = T * 512;
-    const int xs_bytes = T * kTripBytes, w_bytes = (MAXW - 1) * 4 * colb, meta_bytes = (MAXW - 1) * 4 * 64;
+    const int xs_bytes = T * kTripBytes5, w_bytes = (MAXW - 1) * 4 * colb, meta_bytes = (MAXW - 1) * 4 * 64;
     uint32_t* s32 = reinterpret_cast<uint32_t*>(smem);
     for (int i = tid; i < (xs_bytes + w_bytes + meta_bytes) / 4; i += blockDim.x) {
         uint32_t v = src[(i * 7 + blockIdx.x) & 0xFFFFF];
@@ -130,6 +153,28 @@ __global__ void __launch_bounds__(32 * MAXW, 1) trip_kernel(const uint32_t* __re
     const uint32_t scol0 = mb + (2 * h) * 64, scol1 = scol0 + 64, zcol0 = scol0 + 32, zcol1 = scol1 + 32;
     float sink = 0.f;
     const long long t0 = clock64();
+    if (VAR == 5) {
+        const uint32_t wc[4] = {wb + lane * 16, wb + colb + lane * 16, wb + 2 * colb + lane * 16, wb + 3 * colb + lane * 16};
+#pragma unroll 1
+        for (int task = 0; task < ntasks; task++) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+            for (int t = 0; t < T; t++) {
+                ColMeta m[4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) m[c] = col_meta(mb + c * 64, mb + c * 64 + 32, t & 1, lane >> 1);
+                const uint32_t wt[4] = {wc[0] + t * 512, wc[1] + t * 512, wc[2] + t * 512, wc[3] + t * 512};
+                q4_trip4_v5(acc, xs + t * kTripBytes5 + lane * kRowBytes5, wt, m);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                float v = acc[c];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) v = v + __shfl_xor_sync(0xffffffffu, v, d);
+                sink += v;
+            }
+        }
+    } else
 #pragma unroll 1
     for (int task = 0; task < ntasks; task++) {
         unsigned long long acc0 = 0ull, acc1 = 0ull;
@@ -153,7 +198,7 @@ __global__ void __launch_bounds__(32 * MAXW, 1) trip_kernel(const uint32_t* __re
 template <int VAR>
 void run(const char* name, const uint32_t* src, float* out, long long* cyc, int sms) {
     const int T = 4, ntasks = 64;
-    const size_t smem = (size_t)T * kTripBytes + (MAXW - 1) * 4 * T * 512 + (MAXW - 1) * 4 * 64;
+    const size_t smem = (size_t)T * kTripBytes5 + (MAXW - 1) * 4 * T * 512 + (MAXW - 1) * 4 * 64;
     cudaFuncSetAttribute(trip_kernel<VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncAttributes fa;
     cudaFuncGetAttributes(&fa, trip_kernel<VAR>);
@@ -191,5 +236,6 @@ int main() {
     run<2>("v2 FFMA instead of FFMA2", src, out, cyc, sms);
     run<3>("v3 dequant only (+FADD)", src, out, cyc, sms);
     run<4>("v4 FFMA2 accumulate only", src, out, cyc, sms);
+    run<5>("v5 one lane x four columns, FFMA", src, out, cyc, sms);
     return 0;
 }
