@@ -377,7 +377,7 @@ void launch_interp(const Plan& pl, const Op* d_ops, int nops, const Op* one, con
         }
     }
     if (g.opt_trace && d_ops != nullptr && nops + 1 <= 2048) {
-        if (!g.trace) { LQ4_CHECK(cudaMalloc((void**)&g.trace, 8192 * sizeof(unsigned long long))); LQ4_CHECK(cudaMemset(g.trace, 0, 8192 * sizeof(unsigned long long))); }
+        if (!g.trace) { LQ4_CHECK(cudaMalloc((void**)&g.trace, 32768 * sizeof(unsigned long long))); LQ4_CHECK(cudaMemset(g.trace, 0, 32768 * sizeof(unsigned long long))); }
         P.trace = g.trace;
         P.trace_op = g.opt_trace_op;
         g.trace_n = nops + 1;
@@ -580,7 +580,7 @@ int lq4_debug_trace(unsigned long long* out, int* kinds, int max) {
     cudaStreamSynchronize(g.stream);
     const int n = std::min(max, g.trace_n);
     cudaMemcpy(out, g.trace, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost);
-    if (max >= 8192) cudaMemcpy(out + 2048, g.trace + 2048, sizeof(unsigned long long) * 6144, cudaMemcpyDeviceToHost);
+    if (max >= 8192) cudaMemcpy(out + 2048, g.trace + 2048, sizeof(unsigned long long) * (max >= 32768 ? 30720 : 6144), cudaMemcpyDeviceToHost);
     if (kinds && !g.nets.empty()) {
         NetPlan& np = g.nets.begin()->second;
         std::vector<Op> ops(np.nops);

@@ -29,7 +29,7 @@ lib.lq4_set_option(b"trace_op", trace_op)
 for i in range(npos):
     lib.lq4_enqueue_step(C.byref(t), C.byref(s), i + 1, 1)
 assert lib.lq4_stream_synchronize() == 0
-N = 8192
+N = 32768
 ts = (C.c_ulonglong * N)()
 kinds = (C.c_int * N)()
 n = lib.lq4_debug_trace(ts, kinds, N)
@@ -76,3 +76,23 @@ ex = np.array([[ts[2048 + 148 * 8 + b * 16 + k] for k in range(8, 11)] for b in 
 ahead0, ahead1 = ex[:, 0] - ex[:, 2], ex[:, 1] - ex[:, 2]
 print(f"  ring chunks the producer was ahead of this op's first chunk [min/median/max over CTAs]: when x was staged {ahead0.min():.0f}/{np.median(ahead0):.0f}/{ahead0.max():.0f}, "
       f"when warp 0 got its first weights {ahead1.min():.0f}/{np.median(ahead1):.0f}/{ahead1.max():.0f}")
+if os.environ.get("TRACE_DUMP"):
+    print("  per CTA, sorted by SM id: cta sm | arrive passed staged first-weights warp0-done all-done (us)")
+    for b in sorted(range(nb), key=lambda b: smid[b]):
+        print(f"    {b:3d} {smid[b]:3d} | " + " ".join(f"{rel[b, k]:6.2f}" for k in range(6)))
+
+# per consumer warp: first weights and end of its tasks (us after the first CTA past the barrier), median over CTAs
+wm = np.array([[[ts[8192 + b * 32 + w * 2 + k] for k in range(2)] for w in range(11)] for b in range(nb)], dtype=np.float64)
+print("  per warp [median over CTAs]: first weights / left the op (us); 0 = no task")
+for w in range(11):
+    a = wm[:, w, 0]; e = wm[:, w, 1]
+    ok = a > 0
+    if ok.any():
+        print(f"    warp {w:2d}: {np.median((a[ok] - t0) / 1000.0):6.2f} / {np.median((e[ok] - t0) / 1000.0):6.2f}   ({int(ok.sum())} CTAs)")
+    else:
+        print(f"    warp {w:2d}:   -    / {np.median((e - t0) / 1000.0):6.2f}")
+
+pi = np.array([[ts[16384 + b * 32 + k] for k in range(32)] for b in range(nb)], dtype=np.float64)
+if (pi > 0).any():
+    print("  producer: issue time of the op's k-th chunk (us, median over CTAs; builds with -DLQ4_PROD_TRACE):")
+    print("    " + " ".join(f"{np.median((pi[:, k][pi[:, k] > 0] - t0) / 1000.0):6.2f}" for k in range(32) if (pi[:, k] > 0).any()))

@@ -132,7 +132,7 @@ __device__ __forceinline__ void q4_trip4_v5(float (&acc)[4], uint32_t xaddr, con
 static const int kActive[] = {1, 2, 4, 7, 8, 11, 12, 15, 16, 19, 20, 23};
 
 template <int VAR>
-__global__ void __launch_bounds__(32 * MAXW, 1) trip_kernel(const uint32_t* __restrict__ src, float* out, long long* cyc, int T, int ntasks, int active) {
+__global__ void __launch_bounds__(32 * MAXW, 1) trip_kernel(const uint32_t* __restrict__ src, float* out, long long* cyc, int T, int ntasks, int active, int prod) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int colb = T * 512;
@@ -144,7 +144,30 @@ __global__ void __launch_bounds__(32 * MAXW, 1) trip_kernel(const uint32_t* __re
         else if (i >= (xs_bytes + w_bytes) / 4) v = (v & 0x03FF03FFu) | 0x20002000u;   // scales: small fp16, zeros: whatever
         s32[i] = v;
     }
+    // the production kernel's twelfth warp: one lane keeping bulk copies in flight into shared memory (prod = 2: eight 8 KB copies
+    // at a time, about the ring's fill rate; prod = 1: only spinning on an mbarrier that never completes)
+    volatile int* stop = reinterpret_cast<volatile int*>(smem + xs_bytes + w_bytes + meta_bytes);
+    const uint32_t pbar = smem_u32(smem) + xs_bytes + w_bytes + meta_bytes + 64, pring = pbar + 64 + 896;   // 1 KB after the meta area
+    if (tid == 0) { stop[0] = 0; stop[1] = 0; for (int i = 0; i < 8; i++) mbar_init(pbar + i * 8, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
+    if (warp == MAXW - 1) {
+        if (lane != 0 || prod == 0) return;
+        uint64_t policy;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+        if (prod == 1) { while (!*stop) (void)mbar_try_wait(pbar, 0); return; }
+        unsigned n = 0;
+        while (!*stop) {
+            const unsigned sl = n & 7, lap = n >> 3;
+            if (lap > 0) while (!mbar_try_wait(pbar + sl * 8, (lap - 1) & 1)) {}
+            mbar_arrive_expect_tx(pbar + sl * 8, 8192);
+            bulk_g2s(pring + sl * 8192, reinterpret_cast<const uint8_t*>(src) + ((size_t)(n * 148 + blockIdx.x) * 8192 & 0x3FFFFF & ~8191u), 8192, pbar + sl * 8, policy);
+            n++;
+        }
+        for (unsigned k = (n > 8 ? n - 8 : 0); k < n; k++) while (!mbar_try_wait(pbar + (k & 7) * 8, (k >> 3) & 1)) {}      // drain before exit
+        cyc[blockIdx.x * MAXW + MAXW - 1] = (long long)n;
+        return;
+    }
     if (warp >= active) return;
     const uint32_t base = smem_u32(smem);
     const uint32_t xs = base, wb = base + xs_bytes + warp * 4 * colb, mb = base + xs_bytes + w_bytes + warp * 4 * 64;
@@ -191,35 +214,43 @@ __global__ void __launch_bounds__(32 * MAXW, 1) trip_kernel(const uint32_t* __re
         sink += halfwarp_total(acc0) + halfwarp_total(acc1);
     }
     const long long t1 = clock64();
-    if (lane == 0) cyc[blockIdx.x * MAXW + warp] = t1 - t0;
+    if (lane == 0) {
+        cyc[blockIdx.x * MAXW + warp] = t1 - t0;
+        int* done = const_cast<int*>(stop) + 1;
+        if (atomicAdd(done, 1) == active - 1) { *stop = 1; *done = 0; }
+    }
     out[blockIdx.x * blockDim.x + tid] = sink;
 }
 
 template <int VAR>
 void run(const char* name, const uint32_t* src, float* out, long long* cyc, int sms) {
     const int T = 4, ntasks = 64;
-    const size_t smem = (size_t)T * kTripBytes5 + (MAXW - 1) * 4 * T * 512 + (MAXW - 1) * 4 * 64;
+    const size_t smem = (size_t)T * kTripBytes5 + (MAXW - 1) * 4 * T * 512 + (MAXW - 1) * 4 * 64 + 1024 + 8 * 8192;
     cudaFuncSetAttribute(trip_kernel<VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncAttributes fa;
     cudaFuncGetAttributes(&fa, trip_kernel<VAR>);
+    for (int prod : {0, 1, 2})
     for (int active : kActive) {
         if (active > MAXW - 1) continue;
+        if (prod != 0 && active != 7 && active != 11) continue;
         cudaMemset(cyc, 0, sizeof(long long) * sms * MAXW);
-        trip_kernel<VAR><<<sms, 32 * MAXW, smem>>>(src, out, cyc, T, ntasks, active);
+        trip_kernel<VAR><<<sms, 32 * MAXW, smem>>>(src, out, cyc, T, ntasks, active, prod);
         cudaDeviceSynchronize();
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0);
-        trip_kernel<VAR><<<sms, 32 * MAXW, smem>>>(src, out, cyc, T, ntasks, active);
+        trip_kernel<VAR><<<sms, 32 * MAXW, smem>>>(src, out, cyc, T, ntasks, active, prod);
         cudaEventRecord(e1);
         cudaDeviceSynchronize();
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         std::vector<long long> h(sms * MAXW);
         cudaMemcpy(h.data(), cyc, sizeof(long long) * sms * MAXW, cudaMemcpyDeviceToHost);
-        double sum = 0, mx = 0; int n = 0;
-        for (int b = 0; b < sms; b++) for (int w = 0; w < active; w++) { double c = (double)h[b * MAXW + w]; sum += c; if (c > mx) mx = c; n++; }
+        double sum = 0, mx = 0, copies = 0; int n = 0;
+        for (int b = 0; b < sms; b++) { copies += (double)h[b * MAXW + MAXW - 1]; for (int w = 0; w < active; w++) { double c = (double)h[b * MAXW + w]; sum += c; if (c > mx) mx = c; n++; } }
         const double per_trip = sum / n / (ntasks * T);
-        printf("%-34s regs %3d  active warps %2d: %7.0f clk per warp-trip (slowest warp %7.0f), %5.1f weights/clk/SM  [%0.3f ms, err %d]\n", name, fa.numRegs, active, per_trip,
+        printf("%-34s regs %3d  active warps %2d producer %d: %7.0f clk per warp-trip (slowest warp %7.0f), %5.1f weights/clk/SM  [%0.3f ms, err %d", name, fa.numRegs, active, prod, per_trip,
                mx / (ntasks * T), active * 4096.0 / (mx / (ntasks * T)), ms, (int)cudaGetLastError());
+        if (prod == 2) printf(", %.1f B/clk/SM copied", copies / sms * 8192.0 / mx);
+        printf("]\n");
     }
 }
 
