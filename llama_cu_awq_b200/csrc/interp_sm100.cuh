@@ -572,8 +572,8 @@ __device__ void producer_loop(const InterpParams& P, const Op* ops, const Smem& 
                     }
                 }
                 asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(pfill + slot * 4), "r"(pf + 1) : "memory");
-#ifdef LQ4_PROD_TRACE      // diagnosis builds only: when the producer issued each chunk of the traced op (reading the timer costs ~0.15 us)
-                if (P.trace != nullptr && o == P.trace_op) { const int k = (task - t0) * spt + i; if (k < 32) P.trace[16384 + blockIdx.x * 32 + k] = global_ns(); }
+#ifdef LQ4_PROD_TRACE      // diagnosis builds only: when the producer issued each chunk of the traced op (SM clock)
+                if (P.trace != nullptr && o == P.trace_op) { const int k = (task - t0) * spt + i; if (k < 32) P.trace[27136 + blockIdx.x * 32 + k] = (unsigned long long)clock64(); }
 #endif
                 if constexpr (kPrefetchAhead > 0) ahead_step(P, ops, ahead);      // keep the L2 lookahead kPrefetchAhead slots in front
                 if (++slot == S) slot = 0;
@@ -631,11 +631,12 @@ __device__ __forceinline__ unsigned producer_issued(const Ctx& c) {
     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(c.sm.bars + 3584) : "memory");
     return v;
 }
-// development aid: per consumer warp, when its first task's weights were there (k = 0) and when it left the op (k = 1)
+// development aid, SM clock: per consumer warp, when its first task's weights were there (k = 0), when its 1st..5th task was done
+// (k = 1..5) and when it left the op (k = 7).  Record of warp w of CTA b: trace[8192 + b * 128 + w * 8 + k].
 template <int F>
 __device__ __forceinline__ void warp_mark(const CtxT<F>& c, int k) {
     if constexpr (!(F & kDev)) return;
-    if (c.tr != nullptr && c.lane == 0) (c.tr - blockIdx.x * 8 - 2048 + 8192 + blockIdx.x * 32 + c.warp * 2)[k] = global_ns();
+    if (c.tr != nullptr && c.lane == 0 && k < 8) (c.tr - blockIdx.x * 8 - 2048 + 8192 + blockIdx.x * 128 + c.warp * 8)[k] = (unsigned long long)clock64();
 }
 template <int F>
 __device__ __forceinline__ void trace_mark(const CtxT<F>& c, int k) {
@@ -1081,6 +1082,7 @@ __device__ void run_q4(CtxT<F>& c, const Op& op) {
         }
         if (task == t0) { trace_mark(c, 3); cyc_mark(c, 5); if ((F & kDev) && c.tr != nullptr) val_mark(c, 9, producer_issued(c)); }   // warp 0: first task's weights are in shared memory
         if (task == t0 + c.warp) warp_mark(c, 0);
+        const int nth_task = (task - t0) / c.nwc;
         w0 += j * 32 + sw * 16;
         w1 += j * 32 + sw * 16;
         unsigned long long acc0 = 0ull, acc1 = 0ull;
@@ -1101,6 +1103,7 @@ __device__ void run_q4(CtxT<F>& c, const Op& op) {
             rp.slot += c.nwc * spt;
             while (rp.slot >= c.sm.S) { rp.slot -= c.sm.S; rp.lap++; }
         }
+        warp_mark(c, 1 + nth_task < 6 ? 1 + nth_task : 8);
         if (task == t0) { trace_mark(c, 6); cyc_mark(c, 6); }   // warp 0: first task done
         else if (task == t0 + c.nwc) trace_mark(c, 7);    // warp 0: second task done
         // ---- epilogue ----
@@ -1138,7 +1141,7 @@ __device__ void run_q4(CtxT<F>& c, const Op& op) {
         }
     }
     trace_mark(c, 4);                                    // warp 0 has finished its tasks
-    warp_mark(c, 1);
+    warp_mark(c, 7);
     c.qbase += (unsigned)(t1 - t0) * spt;
     c.qtotal += (unsigned)(t1 - t0) * spt;
     c.meta_pending = mb;

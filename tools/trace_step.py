@@ -81,18 +81,19 @@ if os.environ.get("TRACE_DUMP"):
     for b in sorted(range(nb), key=lambda b: smid[b]):
         print(f"    {b:3d} {smid[b]:3d} | " + " ".join(f"{rel[b, k]:6.2f}" for k in range(6)))
 
-# per consumer warp: first weights and end of its tasks (us after the first CTA past the barrier), median over CTAs
-wm = np.array([[[ts[8192 + b * 32 + w * 2 + k] for k in range(2)] for w in range(11)] for b in range(nb)], dtype=np.float64)
-print("  per warp [median over CTAs]: first weights / left the op (us); 0 = no task")
+# per consumer warp (SM clock, relative to this CTA's 'barrier passed'): first weights, task k done, left the op
+CLK = 1965.0
+wm = np.array([[[ts[8192 + b * 128 + w * 8 + k] for k in range(8)] for w in range(11)] for b in range(nb)], dtype=np.float64)
+ref = cy[:, 0]
+print("  per warp, us after the CTA's 'barrier passed' [median over CTAs]: first weights | task 1..5 done | left the op")
 for w in range(11):
-    a = wm[:, w, 0]; e = wm[:, w, 1]
-    ok = a > 0
-    if ok.any():
-        print(f"    warp {w:2d}: {np.median((a[ok] - t0) / 1000.0):6.2f} / {np.median((e[ok] - t0) / 1000.0):6.2f}   ({int(ok.sum())} CTAs)")
-    else:
-        print(f"    warp {w:2d}:   -    / {np.median((e - t0) / 1000.0):6.2f}")
-
-pi = np.array([[ts[16384 + b * 32 + k] for k in range(32)] for b in range(nb)], dtype=np.float64)
+    row = []
+    for k in range(8):
+        v = wm[:, w, k]
+        ok = v > ref        # marks of this step only
+        row.append(f"{np.median((v[ok] - ref[ok]) / CLK):6.2f}" if ok.sum() > nb // 2 else "   -  ")
+    print(f"    warp {w:2d}: {row[0]} | " + " ".join(row[1:6]) + f" | {row[7]}")
+pi = np.array([[ts[27136 + b * 32 + k] for k in range(32)] for b in range(nb)], dtype=np.float64)
 if (pi > 0).any():
-    print("  producer: issue time of the op's k-th chunk (us, median over CTAs; builds with -DLQ4_PROD_TRACE):")
-    print("    " + " ".join(f"{np.median((pi[:, k][pi[:, k] > 0] - t0) / 1000.0):6.2f}" for k in range(32) if (pi[:, k] > 0).any()))
+    print("  producer: issue time of the op's k-th chunk, us after the CTA's 'barrier passed' [median over CTAs] (builds with -DLQ4_PROD_TRACE):")
+    print("    " + " ".join(f"{np.median((pi[:, k] - ref) / CLK):6.2f}" for k in range(32) if (pi[:, k] > 0).any()))
