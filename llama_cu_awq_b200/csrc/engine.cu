@@ -1403,6 +1403,10 @@ int lq4_prefill(Transformer* t, const int* tokens, int batch, int seq, int kv_se
     if (hs != 128 && hs != 64) {
         if (attn_smem > (size_t)g.max_smem) return 1;
         allow_smem(lq4pf::attn_prefill_kernel, attn_smem);
+    } else if (hs == 128) {
+        allow_smem(lq4pf::attn_prefill_mma_kernel<128>, lq4pf::fa_smem_bytes<128>());
+    } else {
+        allow_smem(lq4pf::attn_prefill_mma_kernel<64>, lq4pf::fa_smem_bytes<64>());
     }
     LQ4_CHECK(cudaEventRecord(ev[0], g.stream));
     lq4pf::embed_rows_kernel<<<(unsigned)M, 128, 0, g.stream>>>(W.x, w->token_embedding_table, W.tokens, dim);
@@ -1420,9 +1424,9 @@ int lq4_prefill(Transformer* t, const int* tokens, int batch, int seq, int kv_se
         const float att_alpha = (float)(1.0 / sqrt((double)hs));
         const dim3 fa_grid((seq + lq4pf::kFaQ - 1) / lq4pf::kFaQ, p->n_heads, batch);
         if (hs == 128)
-            lq4pf::attn_prefill_mma_kernel<128><<<fa_grid, 128, 0, g.stream>>>(W.att, W.q, W.k, W.v, seq, p->n_heads, kv_mul, att_alpha);
+            lq4pf::attn_prefill_mma_kernel<128><<<fa_grid, 128, lq4pf::fa_smem_bytes<128>(), g.stream>>>(W.att, W.q, W.k, W.v, seq, p->n_heads, kv_mul, att_alpha);
         else if (hs == 64)
-            lq4pf::attn_prefill_mma_kernel<64><<<fa_grid, 128, 0, g.stream>>>(W.att, W.q, W.k, W.v, seq, p->n_heads, kv_mul, att_alpha);
+            lq4pf::attn_prefill_mma_kernel<64><<<fa_grid, 128, lq4pf::fa_smem_bytes<64>(), g.stream>>>(W.att, W.q, W.k, W.v, seq, p->n_heads, kv_mul, att_alpha);
         else        // other head sizes: the CUDA-core kernel
             lq4pf::attn_prefill_kernel<<<dim3((seq + lq4pf::kPfQ - 1) / lq4pf::kPfQ, p->n_heads, batch), 256, attn_smem, g.stream>>>(
                 W.att, W.q, W.k, W.v, seq, p->n_heads, kv_mul, hs, att_alpha);
@@ -1431,7 +1435,7 @@ int lq4_prefill(Transformer* t, const int* tokens, int batch, int seq, int kv_se
         gemm(W.g, W.xn, &L.wq_gate, dim, hidden, nullptr);
         gemm(W.u, W.xn, &L.wq_up, dim, hidden, nullptr);
         const size_t nh = M * hidden;
-        lq4pf::silu_mul_kernel<<<(unsigned)((nh + 255) / 256), 256, 0, g.stream>>>(W.g, W.g, W.u, nh);
+        lq4pf::silu_mul_kernel<<<(unsigned)((nh / 8 + 255) / 256), 256, 0, g.stream>>>(W.g, W.g, W.u, nh);
         gemm(W.x, W.g, &L.wq_down, hidden, dim, W.x);
     }
     // last position of every sequence: final RMSNorm + classifier (the decode path's fp16 GEMV, one row per sequence)

@@ -337,24 +337,43 @@ __global__ void __launch_bounds__(256) rmsnorm_rows_kernel(half* o, const half* 
 }
 
 // RoPE on q (n_heads) and k (n_kv_heads) rows: pairs (i, i + hs/2), position = row % seq (RoPERotation_kernel, gpu_kernels.h:332-355)
+// 8 consecutive pair indices per thread: 16-byte loads and stores of both halves of the head (hs % 16 == 0)
 __global__ void rope_rows_kernel(half* q, half* k, const float2* __restrict__ tab, int n_heads, int n_kv_heads, int hs, int seq) {
     const int row = blockIdx.x, pos = row % seq;
-    const int half_hs = hs / 2;
-    for (int idx = threadIdx.x; idx < (n_heads + n_kv_heads) * half_hs; idx += blockDim.x) {
-        const int h = idx / half_hs, i = idx - h * half_hs;
+    const int half_hs = hs / 2, per = half_hs / 8;
+    for (int idx = threadIdx.x; idx < (n_heads + n_kv_heads) * per; idx += blockDim.x) {
+        const int h = idx / per, i = (idx - h * per) * 8;
         half* v = (h < n_heads) ? q + (size_t)row * n_heads * hs + h * hs : k + (size_t)row * n_kv_heads * hs + (h - n_heads) * hs;
-        const float2 cs = tab[(size_t)pos * half_hs + i];
-        const float a = __half2float(v[i]), b = __half2float(v[i + half_hs]);
-        v[i] = __float2half_rn(a * cs.x - b * cs.y);
-        v[i + half_hs] = __float2half_rn(a * cs.y + b * cs.x);
+        uint4 lo = *reinterpret_cast<const uint4*>(v + i), hi = *reinterpret_cast<const uint4*>(v + i + half_hs);
+        half* a = reinterpret_cast<half*>(&lo);
+        half* b = reinterpret_cast<half*>(&hi);
+        const float4* cs4 = reinterpret_cast<const float4*>(tab + (size_t)pos * half_hs + i);
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+            const float4 cs = cs4[e >> 1];                 // (cos, sin) of pairs e and e + 1
+            const float a0 = __half2float(a[e]), b0 = __half2float(b[e]), a1 = __half2float(a[e + 1]), b1 = __half2float(b[e + 1]);
+            a[e] = __float2half_rn(a0 * cs.x - b0 * cs.y);         b[e] = __float2half_rn(a0 * cs.y + b0 * cs.x);
+            a[e + 1] = __float2half_rn(a1 * cs.z - b1 * cs.w);     b[e + 1] = __float2half_rn(a1 * cs.w + b1 * cs.z);
+        }
+        *reinterpret_cast<uint4*>(v + i) = lo;
+        *reinterpret_cast<uint4*>(v + i + half_hs) = hi;
     }
 }
 
+// 8 elements per thread (n % 8 == 0: the hidden size is a multiple of 8); the arithmetic of gpu_kernels.h:269-273
 __global__ void silu_mul_kernel(half* out, const half* __restrict__ gate, const half* __restrict__ up, size_t n) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
     if (i < n) {
-        const float g = __half2float(gate[i]);
-        out[i] = __float2half_rn(g * (1.0f / (1.0f + expf(-g))) * __half2float(up[i]));
+        uint4 gv = *reinterpret_cast<const uint4*>(gate + i);
+        const uint4 uv = *reinterpret_cast<const uint4*>(up + i);
+        half* gh = reinterpret_cast<half*>(&gv);
+        const half* uh = reinterpret_cast<const half*>(&uv);
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const float g = __half2float(gh[e]);
+            gh[e] = __float2half_rn(g * (1.0f / (1.0f + expf(-g))) * __half2float(uh[e]));
+        }
+        *reinterpret_cast<uint4*>(out + i) = gv;
     }
 }
 
@@ -430,17 +449,43 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 constexpr int kFaQ = 64, kFaK = 64;
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+template <int HS>
+constexpr int fa_smem_bytes() { return 4 * kFaK * (HS + 8) * 2; }      // K and V tiles, two buffers each
+// Query tiles are taken heaviest first (the last rows of a sequence see the most keys); K/V tiles are double-buffered (the
+// copies of tile i+1 travel while tile i is multiplied); K fragments come from ldmatrix.x4, V fragments from ldmatrix.x4.trans;
+// the softmax runs in the base-2 domain (ex2.approx; scores are rounded to fp16 first, like the decode path); only the tile on
+// the diagonal is masked.
 template <int HS>
 __global__ void __launch_bounds__(128) attn_prefill_mma_kernel(half* out, const half* __restrict__ q, const half* __restrict__ k, const half* __restrict__ v,
                                                                int seq, int n_heads, int kv_mul, float alpha) {
     constexpr int LD = HS + 8;                                     // padded row (halfs): conflict-free fragment loads
-    __shared__ __align__(16) half Ks[kFaK * LD];
-    __shared__ __align__(16) half Vs[kFaK * LD];
-    const int q0 = blockIdx.x * kFaQ, h = blockIdx.y, b = blockIdx.z;
+    extern __shared__ __align__(16) uint8_t fa_smem[];
+    half* Ks = reinterpret_cast<half*>(fa_smem);                   // [2][kFaK][LD]
+    half* Vs = Ks + 2 * kFaK * LD;                                 // [2][kFaK][LD]
+    const int q0 = ((int)gridDim.x - 1 - (int)blockIdx.x) * kFaQ, h = blockIdx.y, b = blockIdx.z;
     const int kvh = h / kv_mul, kv_dim = (n_heads / kv_mul) * HS, dim = n_heads * HS;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const size_t row0 = (size_t)b * seq;
     const int r_lo = q0 + warp * 16 + g, r_hi = r_lo + 8;          // this thread's two query rows
+    const half* kbase = k + row0 * kv_dim + kvh * HS;
+    const half* vbase = v + row0 * kv_dim + kvh * HS;
+    auto load_tile = [&](int buf, int k0) {
+        half* kd = Ks + buf * kFaK * LD;
+        half* vd = Vs + buf * kFaK * LD;
+        for (int idx = tid; idx < kFaK * (HS / 8); idx += 128) {
+            const int r = idx / (HS / 8), c = idx % (HS / 8);
+            const size_t key = (size_t)min(k0 + r, seq - 1);
+            lq4::cp_async16(smem_u32(kd + r * LD + c * 8), kbase + key * kv_dim + c * 8);
+            lq4::cp_async16(smem_u32(vd + r * LD + c * 8), vbase + key * kv_dim + c * 8);
+        }
+        lq4::cp_async_commit();
+    };
+    load_tile(0, 0);
     // Q fragments (A operand), straight from global memory
     uint32_t qa[HS / 16][4];
     {
@@ -457,19 +502,20 @@ __global__ void __launch_bounds__(128) attn_prefill_mma_kernel(half* out, const 
     float o[HS / 8][4];
 #pragma unroll
     for (int d = 0; d < HS / 8; d++) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.0f;
-    float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.0f, l_hi = 0.0f;
+    float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.0f, l_hi = 0.0f;      // running maxima in the base-2 domain
     const int last_key = min(q0 + kFaQ, seq) - 1;
-    for (int k0 = 0; k0 <= last_key; k0 += kFaK) {
-        __syncthreads();                                           // the previous tile is no longer read
-        for (int idx = tid; idx < kFaK * (HS / 8); idx += 128) {
-            const int r = idx / (HS / 8), c = idx % (HS / 8);
-            const int key = min(k0 + r, seq - 1);
-            lq4::cp_async16(smem_u32(Ks + r * LD + c * 8), k + (row0 + key) * kv_dim + kvh * HS + c * 8);
-            lq4::cp_async16(smem_u32(Vs + r * LD + c * 8), v + (row0 + key) * kv_dim + kvh * HS + c * 8);
-        }
-        lq4::cp_async_commit();
-        lq4::cp_async_wait<0>();
+    constexpr float kLog2e = 1.4426950408889634f;
+    // ldmatrix lane addressing: matrix mi = lane / 8, row lane % 8
+    const int lm_row = (lane & 7) + ((lane >> 4) << 3), lm_col = ((lane >> 3) & 1) * 8;      // K: two key blocks x two k halves
+    int it = 0;
+    for (int k0 = 0; k0 <= last_key; k0 += kFaK, it++) {
+        const int buf = it & 1;
+        const bool more = k0 + kFaK <= last_key;
+        if (more) load_tile(buf ^ 1, k0 + kFaK);
+        if (more) lq4::cp_async_wait<1>(); else lq4::cp_async_wait<0>();
         __syncthreads();
+        const half* kt = Ks + buf * kFaK * LD;
+        const half* vt = Vs + buf * kFaK * LD;
         // ---- S = Q K^T (16 rows x 64 keys per warp) ----
         float sacc[kFaK / 8][4];
 #pragma unroll
@@ -477,20 +523,26 @@ __global__ void __launch_bounds__(128) attn_prefill_mma_kernel(half* out, const 
 #pragma unroll
         for (int ks = 0; ks < HS / 16; ks++) {
 #pragma unroll
-            for (int n = 0; n < kFaK / 8; n++) {
-                const half* kr = Ks + (n * 8 + g) * LD + ks * 16 + 2 * t;
-                mma16816(sacc[n], qa[ks], *reinterpret_cast<const uint32_t*>(kr), *reinterpret_cast<const uint32_t*>(kr + 8));
+            for (int n = 0; n < kFaK / 8; n += 2) {
+                uint32_t b0, b1, b2, b3;
+                const uint32_t addr = smem_u32(kt + (n * 8 + lm_row) * LD + ks * 16 + lm_col);
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(addr));
+                mma16816(sacc[n], qa[ks], b0, b1);
+                mma16816(sacc[n + 1], qa[ks], b2, b3);
             }
         }
-        // ---- scale, round like the decode path, causal mask, online softmax ----
+        // ---- scale, round like the decode path, causal mask (diagonal tile only), online softmax in base 2 ----
+        const bool diag = k0 + kFaK > q0;
         float mx_lo = m_lo, mx_hi = m_hi;
 #pragma unroll
         for (int n = 0; n < kFaK / 8; n++) {
 #pragma unroll
             for (int e = 0; e < 4; e++) {
-                const int key = k0 + n * 8 + 2 * t + (e & 1), row = (e < 2) ? r_lo : r_hi;
-                float sv = __half2float(__float2half_rn(sacc[n][e] * alpha));
-                if (key > row || key >= seq) sv = -INFINITY;
+                float sv = __half2float(__float2half_rn(sacc[n][e] * alpha)) * kLog2e;
+                if (diag) {
+                    const int key = k0 + n * 8 + 2 * t + (e & 1), row = (e < 2) ? r_lo : r_hi;
+                    if (key > row || key >= seq) sv = -INFINITY;
+                }
                 sacc[n][e] = sv;
                 if (e < 2) mx_lo = fmaxf(mx_lo, sv); else mx_hi = fmaxf(mx_hi, sv);
             }
@@ -498,13 +550,13 @@ __global__ void __launch_bounds__(128) attn_prefill_mma_kernel(half* out, const 
         mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1)); mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
         mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1)); mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
         // every row of the block sees key 0 in the first tile, so the running maxima are finite from the first tile on
-        const float c_lo = expf(m_lo - mx_lo), c_hi = expf(m_hi - mx_hi);
+        const float c_lo = ex2_approx(m_lo - mx_lo), c_hi = ex2_approx(m_hi - mx_hi);
         m_lo = mx_lo; m_hi = mx_hi;
         float s_lo = 0.0f, s_hi = 0.0f;
         uint32_t pa[kFaK / 16][4];
 #pragma unroll
         for (int n = 0; n < kFaK / 8; n++) {
-            const float p0 = expf(sacc[n][0] - m_lo), p1 = expf(sacc[n][1] - m_lo), p2 = expf(sacc[n][2] - m_hi), p3 = expf(sacc[n][3] - m_hi);
+            const float p0 = ex2_approx(sacc[n][0] - m_lo), p1 = ex2_approx(sacc[n][1] - m_lo), p2 = ex2_approx(sacc[n][2] - m_hi), p3 = ex2_approx(sacc[n][3] - m_hi);
             s_lo += p0 + p1; s_hi += p2 + p3;
             pa[n >> 1][(n & 1) * 2] = pack_h2(p0, p1);
             pa[n >> 1][(n & 1) * 2 + 1] = pack_h2(p2, p3);
@@ -514,17 +566,19 @@ __global__ void __launch_bounds__(128) attn_prefill_mma_kernel(half* out, const 
         l_lo = l_lo * c_lo + s_lo; l_hi = l_hi * c_hi + s_hi;
 #pragma unroll
         for (int d = 0; d < HS / 8; d++) { o[d][0] *= c_lo; o[d][1] *= c_lo; o[d][2] *= c_hi; o[d][3] *= c_hi; }
-        // ---- O += P V ----
+        // ---- O += P V: V fragments for two 8-column blocks per ldmatrix.x4.trans ----
 #pragma unroll
         for (int kk = 0; kk < kFaK / 16; kk++) {
 #pragma unroll
-            for (int d = 0; d < HS / 8; d++) {
-                uint32_t b0, b1;
-                const uint32_t addr = smem_u32(Vs + (kk * 16 + (lane & 15)) * LD + d * 8);
-                asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(addr));
+            for (int d = 0; d < HS / 8; d += 2) {
+                uint32_t b0, b1, b2, b3;
+                const uint32_t addr = smem_u32(vt + (kk * 16 + (lane & 15)) * LD + (d + (lane >> 4)) * 8);
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(addr));
                 mma16816(o[d], pa[kk], b0, b1);
+                mma16816(o[d + 1], pa[kk], b2, b3);
             }
         }
+        __syncthreads();                                           // this buffer is refilled by the next iteration's prefetch
     }
     const float i_lo = 1.0f / l_lo, i_hi = 1.0f / l_hi;
 #pragma unroll
