@@ -72,6 +72,7 @@ struct Engine {
     int opt_opk = 0;        // operator API: 1 = stand-alone kernels chained by programmatic dependent launch instead of one-op launches of the persistent kernel
     int opt_fused = 1;      // run_llama_network: one persistent launch per token (1) or op-by-op like the reference (0)
     int opt_nwc = 0;        // consumer warps per CTA; 0 = choose per model
+    int opt_cls_rpt = 0;    // classifier rows per warp-task (1, 2, 4); 0 = choose by row length (development aid)
     int opt_nslots = 0;     // cap on ring slots; 0 = as many as fit
     int opt_slot_bytes = 0; // ring slot size; 0 = the largest minimum chunk of the model's ops
     std::map<RopeKey, float2*> rope_tabs;
@@ -158,6 +159,7 @@ void ensure_init() {
     if ((env = getenv("LQ4_NWC"))) { g.opt_nwc = atoi(env); if (g.opt_nwc != 0 && g.opt_nwc < 8) g.opt_nwc = 8; }
     if ((env = getenv("LQ4_NOMATH"))) g.opt_nomath = atoi(env);
     if ((env = getenv("LQ4_NSLOTS"))) g.opt_nslots = atoi(env);
+    if ((env = getenv("LQ4_CLS_RPT"))) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4) g.opt_cls_rpt = v; }
     if ((env = getenv("LQ4_SLOT_BYTES"))) g.opt_slot_bytes = atoi(env);
     LQ4_CHECK(cudaMallocHost((void**)&g.fault, 4 * sizeof(int)));
     memset(g.fault, 0, 4 * sizeof(int));
@@ -285,13 +287,16 @@ bool q4_op_shape(Op& op, int K, const int* ncols, int nseg, bool dual) {
     if (op.ntasks % op.au) return false;
     return true;
 }
+constexpr int kMaxChunk = 16384;     // largest ring slot
 bool cls_op_shape(Op& op, int n, int d, int row_stride) {
     if ((n & 7) || (row_stride & 7) || (d & 3) || !aligned16(op.seg[0].w)) return false;
     op.K = n;
     op.T = (n + 255) / 256;
     op.nseg = 1;
     op.seg[0].ncols = d;
-    op.rpt = (n * 2 >= 4096) ? 1 : 4;     // a long row alone keeps a warp busy and takes one ring slot instead of four
+    // rows per warp-task: short rows go four to a slot; long rows two to a task, so that one bulk copy brings 16 KB (the producer
+    // lane issues a copy per ~0.2 us whatever its size: with one 8 KB row per copy the 7B classifier streamed at 4.2 TB/s)
+    op.rpt = (g.opt_cls_rpt > 0) ? g.opt_cls_rpt : (n * 2 < 4096) ? 4 : (n * 4 <= kMaxChunk) ? 2 : 1;      // 13B (10 KB rows): two rows would take two slots, measured slower
     op.ntasks = (d + op.rpt - 1) / op.rpt;
     op.au = 1;
     op.row_stride = row_stride;
@@ -306,7 +311,6 @@ int op_min_chunk(const Op& op) {
 int op_task_chunks(const Op& op) { return op.kind == OP_FFN ? 2 : op.kind == OP_CLS ? op.rpt : 4; }
 // Cut the op's tasks into ring slots: the largest piece of a task (whole, half, quarter) of at most kMaxChunk bytes is one
 // slot, and the ring holds as many of those as fit.  Ops with the same slot size share a ring epoch (interp_sm100.cuh).
-constexpr int kMaxChunk = 16384;
 bool op_set_chunking(Op& op, int ring_bytes) {
     const int per = op_task_chunks(op);             // chunks of minimum size per task
     const int limit = g.opt_slot_bytes > 0 ? std::max(g.opt_slot_bytes, op_min_chunk(op)) : kMaxChunk;
