@@ -499,10 +499,14 @@ def main():
         same = min_over_ranks(same, world) == 1.0          # every rank's TP ids equal its own one-GPU ids (which are the reference's)
         eng.close()
         L = cfg["n_layers"]
-        nx = 4 * L + 1            # cross-GPU hand-overs per token: attention out, o, gate/up, down per layer + the sampler's candidates
+        # cross-GPU hand-overs per token: attention out, o, gate/up, down per layer + the sampler's candidates; from 8 ranks on (or with
+        # LQ4_TP_REPL_O=1) every rank computes the whole o projection and its exchange disappears (engine.cu, opt_tp_repl_o)
+        repl_o = os.environ.get("LQ4_TP_REPL_O")
+        repl_o = (world >= 8) if repl_o is None else (int(repl_o) != 0)
+        nx = (3 if repl_o else 4) * L + 1
         line.update({"value": K / (ms * 1e-3), "ms_per_step": ms / K, "scaling": "strong",
                      "config": {"workload": workload, "l2": "inputs larger than L2 (3.6 GB of weights per step, 1/%d per GPU)" % world,
-                                "parallelism": "tp%d (column split of every matrix, activations exchanged by peer stores over NVLink inside the decode kernel)" % world},
+                                "parallelism": "tp%d (column split of every matrix%s, activations exchanged by peer stores over NVLink inside the decode kernel)" % (world, " but the o projection, which every rank computes in full" if repl_o else "")},
                      "e2e": {"value": (nt - 1) / secs, "unit": "tokens/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 8, "how": e2e_how + " (every rank runs the loop)"},
                      "gpu_launches": K, "roofline": roofline_record(E, cfg, args.model, K, ms, peak, peak_src, share=world),
                      "tp": {"ids_match_single_gpu": bool(same), "ids_checked": K, "exchanges_per_token": nx,
