@@ -350,6 +350,14 @@ def op_timings(eng, lib, E, cfg, peak):
     return roofline_ffn, gemv_op
 
 
+def tp_exchanges(world, n_layers, repl_o_env=None):
+    """Cross-GPU hand-overs per token of the tensor-parallel step: attention out, o, gate/up, down per layer + the sampler's
+    candidates; from 8 ranks on (or with LQ4_TP_REPL_O=1) every rank computes the whole o projection and its exchange
+    disappears (engine.cu, opt_tp_repl_o).  Returns (o projection replicated?, exchanges per token)."""
+    repl_o = (world >= 8) if repl_o_env is None else (int(repl_o_env) != 0)
+    return repl_o, (3 if repl_o else 4) * n_layers + 1
+
+
 def prefill_record(eng, lib, E, cfg, batch=8, seq=2048):
     """BASELINE.json configs[4]: prefill batch 8 x seq 2048 (new capability; the reference feeds prompt tokens through decode).
     Every projection is one dense INT4 -> fp16 GEMM on the tcgen05 tensor cores; reported: the whole pass, and its GEMMs alone
@@ -499,11 +507,7 @@ def main():
         same = min_over_ranks(same, world) == 1.0          # every rank's TP ids equal its own one-GPU ids (which are the reference's)
         eng.close()
         L = cfg["n_layers"]
-        # cross-GPU hand-overs per token: attention out, o, gate/up, down per layer + the sampler's candidates; from 8 ranks on (or with
-        # LQ4_TP_REPL_O=1) every rank computes the whole o projection and its exchange disappears (engine.cu, opt_tp_repl_o)
-        repl_o = os.environ.get("LQ4_TP_REPL_O")
-        repl_o = (world >= 8) if repl_o is None else (int(repl_o) != 0)
-        nx = (3 if repl_o else 4) * L + 1
+        repl_o, nx = tp_exchanges(world, L, os.environ.get("LQ4_TP_REPL_O"))
         line.update({"value": K / (ms * 1e-3), "ms_per_step": ms / K, "scaling": "strong",
                      "config": {"workload": workload, "l2": "inputs larger than L2 (3.6 GB of weights per step, 1/%d per GPU)" % world,
                                 "parallelism": "tp%d (column split of every matrix%s, activations exchanged by peer stores over NVLink inside the decode kernel)" % (world, " but the o projection, which every rank computes in full" if repl_o else "")},

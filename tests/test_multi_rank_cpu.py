@@ -57,6 +57,18 @@ def test_single_rank_aggregation_is_identity():
     assert bench.aggregate_throughput(256, 0.5, 1) == 512.0
 
 
+def test_tp_exchange_count_follows_the_engine_rule():
+    """bench.py reports the cross-GPU hand-overs per token it divides by; the engine replicates the o projection from 8 ranks on
+    (engine.cu, opt_tp_repl_o), or as LQ4_TP_REPL_O says."""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.tp_exchanges(2, 32) == (False, 129)
+    assert bench.tp_exchanges(4, 32) == (False, 129)
+    assert bench.tp_exchanges(8, 32) == (True, 97)
+    assert bench.tp_exchanges(8, 32, "0") == (False, 129)
+    assert bench.tp_exchanges(2, 40, "1") == (True, 121)
+
+
 def test_ids_match_reduction_gloo_world2():
     """bench.py's in-run parity flag of a tensor-parallel run is the MIN over ranks of "my TP ids equal my one-GPU ids":
     one dissenting rank must turn it off for the whole job."""
