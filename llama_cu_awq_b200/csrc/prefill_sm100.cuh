@@ -461,7 +461,7 @@ constexpr int fa_smem_bytes() { return 4 * kFaK * (HS + 8) * 2; }      // K and 
 // the softmax runs in the base-2 domain (ex2.approx; scores are rounded to fp16 first, like the decode path); only the tile on
 // the diagonal is masked.
 template <int HS>
-__global__ void __launch_bounds__(128) attn_prefill_mma_kernel(half* out, const half* __restrict__ q, const half* __restrict__ k, const half* __restrict__ v,
+__global__ void __maxnreg__(168) attn_prefill_mma_kernel(half* out, const half* __restrict__ q, const half* __restrict__ k, const half* __restrict__ v,
                                                                int seq, int n_heads, int kv_mul, float alpha) {
     constexpr int LD = HS + 8;                                     // padded row (halfs): conflict-free fragment loads
     extern __shared__ __align__(16) uint8_t fa_smem[];
