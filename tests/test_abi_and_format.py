@@ -112,3 +112,22 @@ def test_reference_packer_roundtrip_if_built():
     import subprocess
     r = subprocess.run([packer], capture_output=True, text=True)
     assert "config" in (r.stdout + r.stderr).lower() or r.returncode != 0
+
+
+def test_makefile_rebuilds_the_library_when_any_of_its_headers_changes():
+    """Every local header the engine's translation unit includes (directly or through another header) is a prerequisite of
+    the library target: a stale .so after a header-only edit would make GPU results and sources disagree silently."""
+    import re
+    csrc = os.path.join(ROOT, "llama_cu_awq_b200", "csrc")
+    seen, todo = set(), ["engine.cu"]
+    while todo:
+        f = todo.pop()
+        for inc in re.findall(r'#include "([^"]+)"', open(os.path.join(csrc, f)).read()):
+            path = os.path.normpath(os.path.join(os.path.dirname(f), inc))
+            if path not in seen and os.path.exists(os.path.join(csrc, path)):
+                seen.add(path)
+                todo.append(path)
+    mk = open(os.path.join(csrc, "Makefile")).read()
+    hdrs = re.search(r"^HDRS := (.*)$", mk, re.M).group(1).split()
+    missing = sorted(h for h in seen if os.path.normpath(h) not in {os.path.normpath(x) for x in hdrs})
+    assert not missing, f"Makefile HDRS lacks {missing}"
